@@ -1,0 +1,11 @@
+// ORACLE (test infrastructure) — stage entry points used by the frame driver.
+#pragma once
+#include "jxo_frame.h"
+
+namespace jxo {
+const EncTables& GetTables();
+void InitialQuantField(Frame* f);       // U2  (jxo_aq.cc)
+void AdjustQuantField(Frame* f);        // U2  (jxo_aq.cc)
+void AcStrategySearch(Frame* f);        // U4 + H8/H9 (jxo_acs.cc)
+bool EntropyCodeFrame(Frame* f);        // U6-U9 (jxo_entropy.cc, jxo_bitstream.cc)
+}  // namespace jxo

@@ -1,0 +1,13 @@
+"""jxlb200 — B200-native JPEG XL lossy (VarDCT) encode hot path.
+
+Host-side mirror of the one encoder call the thesis harness makes,
+``DockerManager::execute_cjxl(input_file, output_file, distance, effort)``
+(benchmark-jpegxl/src/docker_manager.rs:100-137), over the C ABI in
+``include/jxlb200.h`` (``libjxlb200.so``).  There is no CPU fallback: importing
+works anywhere, but creating an encoder without an sm_100 GPU raises.
+"""
+from .encoder import (  # noqa: F401
+    Encoder, EncodeError, Stats, PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY,
+    PROPOSAL_COMBINED, FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, STAGES, frame_dims, library_path, load_library,
+)
+from .synth import synth_image, synth_batch  # noqa: F401

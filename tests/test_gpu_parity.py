@@ -1,0 +1,89 @@
+"""GPU parity: every intermediate of the CUDA path against the CPU oracle on the same seeded
+inputs, through the C ABI.  Bar: bit-exact (integers AND floats: both sides follow the same
+operation order, fmaf only where written)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FLOAT_STAGES = ("xyb", "mask1x1", "qf_float", "mask", "homog")
+INT_STAGES = ("quant_params", "raw_qf", "dc_quant", "nzeros")
+
+
+def _bits(a):
+    return a.view(np.uint8)
+
+
+def _valid_coeffs(c, d):
+    """keeps only the block slots that exist in the frame (edge groups have unused slots)"""
+    c = c.reshape(d["gys"], d["gxs"], 32, 32, 3, 64)
+    full = c.transpose(0, 2, 1, 3, 4, 5).reshape(d["gys"] * 32, d["gxs"] * 32, 3, 64)
+    return full[: d["bys"], : d["bxs"]]
+
+
+def compare_all(pkg, oracle, enc, img, distance, effort, proposal, flags, stages):
+    enc.encode(img, distance, effort, proposal, flags)
+    ora = oracle.encode(img, distance, effort, proposal, flags)
+    assert ora.error == ""
+    d = pkg.frame_dims(img.shape[1], img.shape[0])
+    for st in stages:
+        a, b = enc.dump(st), ora.dump(st)
+        assert a.shape == b.shape, st
+        if st == "coeffs":
+            a, b = _valid_coeffs(a, d), _valid_coeffs(b, d)
+        if st in FLOAT_STAGES:
+            # north star tolerance for XYB / DCT outputs is 1e-5 relative; we require bit equality
+            same = _bits(np.ascontiguousarray(a)) == _bits(np.ascontiguousarray(b))
+            if not same.all():
+                bad = np.flatnonzero(~(a == b) & ~(np.isnan(a) & np.isnan(b)))
+                assert bad.size == 0, f"{st}: {bad.size} mismatches, first at {bad[:5]}: {a[bad[:5]]} vs {b[bad[:5]]}"
+        else:
+            assert np.array_equal(a, b), f"{st}: {np.count_nonzero(a != b)} mismatches"
+
+
+@pytest.mark.parametrize("w,h", [(512, 512), (100, 60), (8, 8), (264, 40), (1, 1), (257, 9)])
+@pytest.mark.parametrize("flags", [1, 3])
+def test_stage_parity_dct8(pkg, oracle, encoder, w, h, flags):
+    img = pkg.synth_image(w, h, w * 7 + h)
+    compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, flags, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+
+
+@pytest.mark.parametrize("distance", [0.5, 1.0, 1.5, 3.0, 8.0, 14.0])
+def test_stage_parity_distances(pkg, oracle, encoder, distance):
+    img = pkg.synth_image(320, 256, 11)
+    compare_all(pkg, oracle, encoder, img, distance, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+
+
+@pytest.mark.parametrize("effort", [3, 5, 9])
+def test_stage_parity_efforts(pkg, oracle, encoder, effort):
+    img = pkg.synth_image(200, 136, 5)
+    compare_all(pkg, oracle, encoder, img, 1.0, effort, 0, 1, INT_STAGES + ("coeffs",))
+
+
+def test_extreme_images(pkg, oracle, encoder):
+    for fill in (0, 255):
+        img = np.full((64, 72, 3), fill, dtype=np.uint8)
+        compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, size=(72, 96, 3), dtype=np.uint8)
+    compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+
+
+def test_error_behaviour(pkg, encoder):
+    img = pkg.synth_image(16, 16, 0)
+    for kwargs in (dict(distance=0.0), dict(effort=0), dict(effort=10), dict(proposal=7)):
+        with pytest.raises(pkg.EncodeError):
+            encoder.encode(img, **kwargs)
+    with pytest.raises(pkg.EncodeError):
+        encoder.encode(np.zeros((4, 4), dtype=np.uint8))
+    encoder.encode(img)   # the context stays usable after an error (skip-and-continue)
+
+
+def test_strided_input(pkg, oracle, encoder):
+    big = pkg.synth_image(300, 80, 2)
+    view = big[:, 10:210, :]          # row stride larger than 3*width
+    enc_bytes = encoder.encode(view, 1.0, 7, 0, 1)
+    a = encoder.dump("coeffs")
+    ora = oracle.encode(np.ascontiguousarray(view), 1.0, 7, 0, 1)
+    d = pkg.frame_dims(200, 80)
+    assert np.array_equal(_valid_coeffs(a, d), _valid_coeffs(ora.dump("coeffs"), d))

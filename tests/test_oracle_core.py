@@ -1,0 +1,109 @@
+"""CPU tests of the oracle's building blocks (no GPU)."""
+import numpy as np
+import pytest
+
+
+def dct_ref_1d(x):
+    n = len(x)
+    k = np.arange(n)[:, None]
+    i = np.arange(n)[None, :]
+    m = np.cos(np.pi * (2 * i + 1) * k / (2 * n)) * np.where(k == 0, 1.0, np.sqrt(2.0)) / n
+    return m @ x
+
+
+@pytest.mark.parametrize("rows,cols", [(8, 8), (16, 16), (32, 32), (16, 8), (8, 16), (32, 16), (16, 32), (4, 4), (8, 4), (4, 8)])
+def test_dct2d_matches_definition(oracle, rows, cols):
+    import ctypes
+    rng = np.random.default_rng(rows * 100 + cols)
+    px = rng.random((rows, cols), dtype=np.float32)
+    out = np.zeros(rows * cols, dtype=np.float32)
+    oracle.lib.jxo_dct2d(px.ctypes.data, cols, rows, cols, out.ctypes.data)
+    ref = np.apply_along_axis(dct_ref_1d, 1, px.astype(np.float64))   # horizontal
+    ref = np.apply_along_axis(dct_ref_1d, 0, ref)                      # vertical -> ref[vf][hf]
+    got = out.reshape(cols, rows).T if rows >= cols else out.reshape(rows, cols)
+    assert np.abs(got - ref).max() < 2e-6
+    # DC = mean
+    assert abs(out[0] - px.mean()) < 1e-6
+    back = np.zeros((rows, cols), dtype=np.float32)
+    oracle.lib.jxo_idct2d(out.ctypes.data, rows, cols, back.ctypes.data, cols)
+    assert np.abs(back - px).max() < 5e-6
+
+
+@pytest.mark.parametrize("strategy,rows,cols", [(0, 8, 8), (3, 8, 8), (12, 8, 8), (13, 8, 8), (4, 16, 16), (5, 32, 32),
+                                                (6, 16, 8), (7, 8, 16), (10, 32, 16), (11, 16, 32)])
+def test_transform_roundtrip(oracle, strategy, rows, cols):
+    rng = np.random.default_rng(strategy)
+    px = rng.random((rows, cols), dtype=np.float32)
+    coef = oracle.transform(strategy, px)
+    back = oracle.inverse_transform(strategy, coef, rows, cols)
+    assert np.abs(back - px).max() < 1e-5
+    assert abs(coef[0] - px.mean()) < 1e-6   # coefficient 0 carries the mean for every strategy
+
+
+def test_natural_order_dct8_is_zigzag(oracle):
+    order = oracle.natural_order(0)
+    assert list(order[:16]) == [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5]
+    assert sorted(order) == list(range(64))
+    for s in (4, 5, 6, 7, 10, 11):
+        o = oracle.natural_order(s)
+        assert sorted(o) == list(range(len(o)))
+
+
+def test_quant_weights_dct8(oracle):
+    w = oracle.quant_weights(0)
+    assert w.shape == (3, 64)
+    assert abs(w[0, 0] - 3150.0) < 1e-3 and abs(w[1, 0] - 560.0) < 1e-3 and abs(w[2, 0] - 512.0) < 1e-3
+    assert np.all(w > 0)
+    # symmetric in (x, y) for a square transform, non-increasing along the first row
+    for c in range(3):
+        m = w[c].reshape(8, 8)
+        assert np.allclose(m, m.T, rtol=1e-6)
+    assert np.all(np.diff(w[1].reshape(8, 8)[0]) <= 1e-3)
+
+
+def test_srgb_lut_and_cbrt(oracle):
+    lut = np.zeros(256, dtype=np.float32)
+    oracle.lib.jxo_srgb_lut(lut.ctypes.data)
+    v = np.arange(256) / 255.0
+    exact = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    assert np.abs(lut - exact).max() < 2e-6       # within 1e-5 of the exact curve
+    for x in (0.0, 1e-6, 0.0037930732, 0.05, 0.5, 1.0, 1.3):
+        assert abs(oracle.lib.jxo_cbrt(x) - np.cbrt(x)) <= 1e-6 * max(1.0, np.cbrt(x))
+
+
+def test_xyb_known_values(oracle, pkg):
+    img = np.zeros((8, 8, 3), dtype=np.uint8)
+    img[:, 4:, :] = 255
+    f = oracle.encode(img, 1.0, 7, 0, 3)
+    d = oracle.dims(8, 8)
+    xyb = f.dump("xyb").reshape(3, d["ys_pad"], d["pitch"])
+    # black: X = 0, Y ~ 0, B ~ 0 ; white: X = 0 (L == M), Y = B = cbrt(1 + bias) - cbrt(bias)
+    assert abs(xyb[0, 0, 0]) < 1e-6 and abs(xyb[1, 0, 0]) < 1e-6 and abs(xyb[2, 0, 0]) < 1e-6
+    white = np.cbrt(1.0 + 0.0037930732552754493) - np.cbrt(0.0037930732552754493)
+    assert abs(xyb[1, 0, 7] - white) < 2e-6 and abs(xyb[2, 0, 7] - white) < 2e-6 and abs(xyb[0, 0, 7]) < 1e-6
+    assert np.all(xyb[:, :, 8:] == 0)             # pitch padding is zero-filled
+
+
+def test_oracle_frame_smoke(oracle, pkg):
+    img = pkg.synth_image(100, 60, 1)            # ragged: not a multiple of 8
+    f = oracle.encode(img, 1.0, 7, 0, 1)
+    assert f.error == ""
+    d = oracle.dims(100, 60)
+    assert (d["xs_pad"], d["ys_pad"], d["bxs"], d["bys"]) == (104, 64, 13, 8)
+    qp = f.dump("quant_params")
+    assert qp[0] >= 1 and qp[1] >= 1
+    raw = f.dump("raw_qf")
+    assert raw.min() >= 1 and raw.max() <= 256
+    coeffs = f.dump("coeffs").reshape(d["num_groups"], 1024, 3, 64)
+    assert np.all(coeffs[:, :, :, 0] == 0)       # DC position is carried by the DC image
+    nz = f.dump("nzeros").reshape(3, d["bys"], d["bxs"])
+    # nzeros must equal the count of non-zero AC coefficients of each block (Y is slot 0)
+    got = (coeffs[0, :, 0, :] != 0).sum(axis=1).reshape(32, 32)[: d["bys"], : d["bxs"]]
+    assert np.array_equal(got, nz[1])
+
+
+def test_oracle_rejects_bad_params(oracle, pkg):
+    img = pkg.synth_image(16, 16, 0)
+    assert oracle.encode(img, 0.0, 7).error != ""
+    assert oracle.encode(img, 1.0, 0).error != ""
+    assert oracle.encode(img, 1.0, 7, 9).error != ""

@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — VarDCT encode throughput (MP/s) of the B200 path, with the roofline of its
+dominant kernel and the CPU baseline beside it.
+
+  python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                   (CPU arm: the oracle on the host cores)
+
+A step = one encode of one synthetic image of the workload (BASELINE.json configs[1]:
+3840x2160 RGB8, distance 1.0, fixed DCT8 strategy) per rank.  `value` is measured with the
+image resident in HBM (jxlb200_encode_device, CUDA events on the encoder's stream);
+`e2e` goes through jxlb200_encode with HOST buffers (pinned staging + H2D + kernels + D2H
+of the codestream inside the timed region).  Ranks shard by image (no data-path collective):
+weak scaling; NCCL only gathers the per-rank times.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "jpeg-xl-lossy-image-compression-thesis_b200"
+
+WORKLOADS = {
+    # name: (width, height, distance, effort, proposal, flags)
+    "4k_dct8_d1": (3840, 2160, 1.0, 7, 0, 1),
+    "4k_full_d1": (3840, 2160, 1.0, 7, 0, 0),
+    "8k_partitioning": (7680, 4320, 1.0, 7, 1, 0),
+    "1080p_combined": (1920, 1080, 1.0, 7, 3, 0),
+    "512_d1": (512, 512, 1.0, 7, 0, 0),
+}
+# algorithmic bytes per pixel of each pipeline stage (DESIGN.md "Kernels")
+STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
+STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
+               "dc": 9, "assemble": 10, "d2h": 11}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_throughput(workload, budget_images, threads):
+    """Times the CPU oracle (oracle/_build/libjxo.so — the repo's scalar restatement; libjxl itself is
+    not available offline) on `budget_images` images of the workload using `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    pkg = importlib.import_module(PKG)
+    w, h, dist, effort, proposal, flags = WORKLOADS[workload]
+    ora = oracle_lib.load(rebuild=not os.path.exists(oracle_lib.SO))
+    imgs = [pkg.synth_image(w, h, 1000 + i) for i in range(min(budget_images, 2))]
+    done = []
+
+    def work(k):
+        f = ora.encode(imgs[k % len(imgs)], dist, effort, proposal, flags)
+        assert f.error == "", f.error
+        done.append(len(f.dump("codestream")))
+        f.close()
+
+    t0 = time.perf_counter()
+    pending = list(range(budget_images))
+    running = []
+    while pending or running:
+        while pending and len(running) < threads:
+            th = threading.Thread(target=work, args=(pending.pop(),))
+            th.start()
+            running.append(th)
+        running[0].join()
+        running.pop(0)
+    dt = time.perf_counter() - t0
+    return budget_images * w * h / 1e6 / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on the host cores.  The reference's own
+    encoder (libjxl behind `cjxl`, docker_manager.rs:136) cannot be built or installed offline, so this
+    arm times the oracle port with one image per host thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    w, h, dist, effort, proposal, flags = WORKLOADS[args.workload]
+    per_step = max(1, min(cores, 8))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_oracle_throughput(args.workload, per_step, per_step)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = statistics.mean(v for v, _ in vals)
+    ms = statistics.mean(dt for _, dt in vals) * 1e3
+    line = {
+        "impl": "reference", "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "width": w, "height": h, "distance": dist, "effort": effort,
+                   "proposal": proposal, "flags": flags},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": per_step, "kind": "port",
+                         "sample": f"{per_step} images of {w}x{h} per step, one oracle encode per host thread "
+                                   "(own CPU restatement; libjxl/cjxl is not installable offline)"},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = importlib.import_module(PKG)
+    w, h, distance, effort, proposal, flags = WORKLOADS[args.workload]
+    mp = w * h / 1e6
+    n_img = 4                                    # distinct inputs per rank, rotated
+    imgs = [pkg.synth_image(w, h, rank * 16 + i) for i in range(n_img)]
+    d_imgs = [torch.from_numpy(im).cuda() for im in imgs]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    enc = pkg.Encoder(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, device time by CUDA events on the encoder's stream ----
+    for i in range(args.warmup):
+        enc.encode_device(d_imgs[i % n_img].data_ptr(), w, h, 3 * w, distance, effort, proposal, flags)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, stage_ms, launches = [], [], 0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 255)                     # L2 flush between timed iterations (untimed)
+        torch.cuda.synchronize()
+        st = enc.encode_device(d_imgs[i % n_img].data_ptr(), w, h, 3 * w, distance, effort, proposal, flags)
+        dev_ms.append(st.total_ms)
+        stage_ms.append(list(st.stage_ms))
+        launches += st.kernel_launches
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    total_ms = float(sum(dev_ms))
+    last_stats = st
+
+    # ---- e2e: host buffers through jxlb200_encode, wall clock around the calls ----
+    for i in range(args.warmup):
+        enc.encode(imgs[i % n_img], distance, effort, proposal, flags)
+    barrier()
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for i in range(args.steps):
+        data, st2 = enc.encode(imgs[i % n_img], distance, effort, proposal, flags)
+        out_bytes += len(data)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = world * mp / (ms_per_step / 1e3)
+        e2e_value = world * mp * args.steps / e2e_s
+        # roofline of the dominant kernel stage (largest mean CUDA-event time among the HBM-bound stages)
+        mean_stage = np.mean(np.array(stage_ms), axis=0)
+        peak, peak_kind = measured_peak_gbs()
+        dom = max(STAGE_BYTES_PER_PX, key=lambda s: mean_stage[STAGE_INDEX[s]])
+        dom_ms = float(mean_stage[STAGE_INDEX[dom]])
+        achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_px": STAGE_BYTES_PER_PX[dom], "kernel_ms": dom_ms,
+                "stage_ms": {k: float(mean_stage[v]) for k, v in STAGE_INDEX.items()}}
+        line = {
+            "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "distance": distance, "effort": effort,
+                       "proposal": proposal, "flags": flags, "images_per_rank_per_step": 1,
+                       "l2": "flushed between timed iterations (256 MiB fill, untimed)",
+                       "parallelism": f"image-sharded x{world}, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": 3 * w * h,
+                    "d2h_bytes_per_step": out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "bpp": last_stats.bpp, "codestream_bytes": last_stats.codestream_bytes,
+            "wall_s_value_loop": wall_s,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = 1
+            v, dt = cpu_oracle_throughput(args.workload, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
+                                    "sample": f"2 images of {w}x{h}, scalar oracle, 1 thread, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,6 +77,7 @@ typedef struct {
   uint32_t acs_histogram[27];   /* first blocks per AcStrategy code               */
   float stage_ms[16];           /* CUDA-event time per pipeline stage (JXLB200_T_*) */
   float total_ms;               /* device time H2D .. D2H                          */
+  uint32_t kernel_launches;     /* CUDA kernels launched by this encode            */
 } jxlb200_stats;
 
 enum {

@@ -12,6 +12,8 @@
 
 namespace jxlb {
 
+thread_local unsigned g_kernel_launches = 0;
+
 #define CUDA_OK(call)                                                                     \
   do {                                                                                    \
     cudaError_t e_ = (call);                                                              \
@@ -117,6 +119,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
   if (!Reserve(fd, err)) return false;
   params_ = p;
   have_frame_ = false;
+  g_kernel_launches = 0;
   const size_t plane = (size_t)fd.ys_pad * fd.pitch;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   float* X = d_xyb_.p; float* Y = X + plane; float* B = Y + plane;
@@ -166,6 +169,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
     stats->num_groups = fd.num_groups; stats->num_dc_groups = fd.num_dc_groups;
     QuantDev q;
     CUDA_OK(cudaMemcpy(&q, d_q_.p, sizeof(q), cudaMemcpyDeviceToHost));
+    stats->kernel_launches = g_kernel_launches;
     stats->global_scale = q.global_scale; stats->quant_dc = q.quant_dc;
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_[0], ev_[1]); stats->stage_ms[JXLB200_T_H2D] = ms;

@@ -294,22 +294,27 @@ __global__ void k_raw_qf(const float* __restrict__ qf, const uint8_t* __restrict
 void launch_aq(const float* x, const float* y, const float* b, const FrameDim& fd, float distance, float* mask1x1,
                float* pre, float* qf, float* mask, cudaStream_t s) {
   dim3 g1((fd.pitch + 127) / 128, (fd.ys_pad + 31) / 32);
+  ++g_kernel_launches;
   k_aq_pre<<<g1, 256, 0, s>>>(y, fd, mask1x1, pre);
   dim3 g2((fd.bxs + 31) / 32, fd.bys);
+  ++g_kernel_launches;
   k_aq_block<<<g2, 256, 0, s>>>(x, y, b, pre, fd, distance, qf, mask);
 }
 
 void launch_fill(float* p, size_t n, float v, cudaStream_t s) {
+  ++g_kernel_launches;
   k_fill<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
 }
 
 void launch_quant_params(const float* qf, size_t n, float quant_dc, QuantDev* q, cudaStream_t s) {
+  ++g_kernel_launches;
   k_quant_params<<<1, 1024, 0, s>>>(qf, n, quant_dc, q);
 }
 
 void launch_raw_qf(const float* qf, const uint8_t* acs, const FrameDim& fd, const QuantDev* q, const uint8_t* cvx,
                    const uint8_t* cvy, int32_t* raw, cudaStream_t s) {
   dim3 g((fd.bxs + 127) / 128, fd.bys);
+  ++g_kernel_launches;
   k_raw_qf<<<g, 128, 0, s>>>(qf, acs, fd, q, cvx, cvy, raw);
 }
 

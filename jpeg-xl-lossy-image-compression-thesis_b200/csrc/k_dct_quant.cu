@@ -261,6 +261,7 @@ void launch_dct8_quant(const float* x, const float* y, const float* b, const Fra
                        float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
                        uint8_t* nzeros, uint8_t* lastpos, cudaStream_t s) {
   dim3 grid(fd.gxs, (fd.bys + kRowsPerCta - 1) / kRowsPerCta);
+  ++g_kernel_launches;
   k_dct8_quant<<<grid, 256, 0, s>>>(x, y, b, fd, qd, weights, dequant_y, izz, cmap, x_qm_mul, b_qm_mul, adjust, raw_qf,
                                     coeffs, dc_quant, nzeros, lastpos);
 }

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X
 void launch_homogeneity(const float* x, const float* y, const float* b, const FrameDim& fd, float distance,
                         float* out, cudaStream_t s) {
   dim3 grid((fd.bxs + 31) / 32, fd.bys);
+  ++g_kernel_launches;
   k_homogeneity<<<grid, 256, 0, s>>>(x, y, b, fd, distance, out);
 }
 

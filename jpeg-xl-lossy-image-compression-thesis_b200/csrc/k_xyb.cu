@@ -69,6 +69,7 @@ void launch_rgb8_to_xyb(const uint8_t* d_rgb, size_t stride, int w, int h, const
                         float* x, float* y, float* b, cudaStream_t s) {
   const int groups = fd.pitch / 4;
   dim3 grid((groups + 127) / 128, fd.ys_pad);
+  ++g_kernel_launches;
   k_rgb8_to_xyb<<<grid, 128, 0, s>>>(d_rgb, stride, w, h, fd, d_lut, x, y, b);
 }
 

@@ -3,6 +3,8 @@
 #include "jxl_common.cuh"
 
 namespace jxlb {
+// number of kernels launched by this thread (reported as jxlb200_stats.kernel_launches)
+extern thread_local unsigned g_kernel_launches;
 // K1 (k_xyb.cu)
 void launch_rgb8_to_xyb(const uint8_t* d_rgb, size_t stride, int w, int h, const FrameDim& fd, const float* d_lut,
                         float* x, float* y, float* b, cudaStream_t s);

@@ -52,7 +52,7 @@ class _Stats(ctypes.Structure):
                 ("height", ctypes.c_uint32), ("num_groups", ctypes.c_uint32), ("num_dc_groups", ctypes.c_uint32),
                 ("global_scale", ctypes.c_uint32), ("quant_dc", ctypes.c_uint32), ("num_tokens", ctypes.c_uint64),
                 ("num_clusters", ctypes.c_uint32), ("acs_histogram", ctypes.c_uint32 * 27),
-                ("stage_ms", ctypes.c_float * 16), ("total_ms", ctypes.c_float)]
+                ("stage_ms", ctypes.c_float * 16), ("total_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32)]
 
 
 @dataclass
@@ -70,12 +70,13 @@ class Stats:
     acs_histogram: list = field(default_factory=list)
     stage_ms: list = field(default_factory=list)
     total_ms: float = 0.0
+    kernel_launches: int = 0
 
     @classmethod
     def _from_c(cls, s: _Stats) -> "Stats":
         return cls(int(s.codestream_bytes), float(s.bpp), int(s.width), int(s.height), int(s.num_groups),
                    int(s.num_dc_groups), int(s.global_scale), int(s.quant_dc), int(s.num_tokens),
-                   int(s.num_clusters), list(s.acs_histogram), list(s.stage_ms), float(s.total_ms))
+                   int(s.num_clusters), list(s.acs_histogram), list(s.stage_ms), float(s.total_ms), int(s.kernel_launches))
 
 
 def library_path() -> str:

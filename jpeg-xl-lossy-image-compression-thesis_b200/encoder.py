@@ -28,7 +28,7 @@ STAGES = {
     9: ("dc_quant", np.int16), 10: ("nzeros", np.uint8), 11: ("tokens", np.uint32), 12: ("histograms", np.uint32),
     13: ("context_map", np.uint8), 14: ("group_streams", np.uint8), 15: ("codestream", np.uint8),
     16: ("mask", np.float32), 17: ("cmap", np.int8), 18: ("token_offsets", np.uint32),
-    19: ("group_offsets", np.uint32), 20: ("acs_entropy", np.float32),
+    19: ("group_offsets", np.uint32), 20: ("acs_entropy", np.float32), 21: ("num_clusters", np.int32),
 }
 STAGE_ID = {v[0]: k for k, v in STAGES.items()}
 

@@ -21,6 +21,12 @@ void* jxo_encode(const uint8_t* rgb, int w, int h, size_t stride, const JxoParam
   EncodeFrame(rgb, w, h, stride, pp, f);
   return f;
 }
+// self-decoder: parses a codestream back into the integer stages (dc_quant, acs, raw_qf, coeffs, ...)
+void* jxo_decode(const uint8_t* data, size_t size) {
+  Frame* f = new Frame();
+  DecodeCodestream(data, size, f);
+  return f;
+}
 const char* jxo_error(void* h) { return ((Frame*)h)->error.c_str(); }
 void jxo_free(void* h) { delete (Frame*)h; }
 
@@ -64,6 +70,7 @@ size_t jxo_dump(void* h, int stage, void* dst, size_t cap) {
     case kStageGroupOffsets: return CopyOut(f->group_offsets, dst, cap);
     case kStageGroupStreams: return CopyOut(f->group_streams, dst, cap);
     case kStageCodestream: return CopyOut(f->codestream, dst, cap);
+    case 21: { const int32_t v[1] = {f->num_clusters}; if (dst && cap >= 4) memcpy(dst, v, 4); return 4; }
     default: return 0;
   }
 }

@@ -50,6 +50,7 @@ struct Frame {
   std::vector<uint32_t> group_offsets;  // num_groups + 1 (bytes)
   std::vector<uint8_t> group_streams;
   std::vector<uint8_t> codestream;
+  int num_clusters = 0;
   std::string error;
 };
 

@@ -7,5 +7,6 @@ const EncTables& GetTables();
 void InitialQuantField(Frame* f);       // U2  (jxo_aq.cc)
 void AdjustQuantField(Frame* f);        // U2  (jxo_aq.cc)
 void AcStrategySearch(Frame* f);        // U4 + H8/H9 (jxo_acs.cc)
-bool EntropyCodeFrame(Frame* f);        // U6-U9 (jxo_entropy.cc, jxo_bitstream.cc)
+bool EntropyCodeFrame(Frame* f);        // U6-U9 (jxo_entropy.cc, jxo_modular.cc, jxo_bitstream.cc)
+bool DecodeCodestream(const uint8_t* data, size_t size, Frame* f);  // self-decoder (jxo_decode.cc)
 }  // namespace jxo

@@ -16,7 +16,7 @@ STAGES = {
     9: ("dc_quant", np.int16), 10: ("nzeros", np.uint8), 11: ("tokens", np.uint32), 12: ("histograms", np.uint32),
     13: ("context_map", np.uint8), 14: ("group_streams", np.uint8), 15: ("codestream", np.uint8),
     16: ("mask", np.float32), 17: ("cmap", np.int8), 18: ("token_offsets", np.uint32),
-    19: ("group_offsets", np.uint32), 20: ("acs_entropy", np.float32),
+    19: ("group_offsets", np.uint32), 20: ("acs_entropy", np.float32), 21: ("num_clusters", np.int32),
 }
 STAGE_ID = {v[0]: k for k, v in STAGES.items()}
 
@@ -36,6 +36,8 @@ class Oracle:
         vp = ctypes.c_void_p
         lib.jxo_encode.restype = vp
         lib.jxo_encode.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(Params)]
+        lib.jxo_decode.restype = vp
+        lib.jxo_decode.argtypes = [vp, ctypes.c_size_t]
         lib.jxo_error.restype = ctypes.c_char_p
         lib.jxo_error.argtypes = [vp]
         lib.jxo_free.argtypes = [vp]
@@ -68,6 +70,11 @@ class Oracle:
         p = Params(distance, effort, proposal, flags)
         h = self.lib.jxo_encode(image.ctypes.data, image.shape[1], image.shape[0], image.strides[0], ctypes.byref(p))
         return Frame(self, h)
+
+    def decode(self, codestream):
+        """self-decoder: codestream bytes -> Frame holding dc_quant / acs / raw_qf / coeffs / nzeros"""
+        buf = np.frombuffer(bytes(codestream), dtype=np.uint8)
+        return Frame(self, self.lib.jxo_decode(buf.ctypes.data, buf.size))
 
     def dims(self, w, h):
         d = (ctypes.c_int32 * 16)()

@@ -1,0 +1,76 @@
+"""CPU tests of the oracle's entropy stage (U6-U9): the emitted codestream must parse with the
+independent self-decoder (tier T2: no djxl exists offline) and give back exactly the integers
+that were coded — quantised DC, AC strategy, quant field, coefficients, non-zero counts."""
+import numpy as np
+import pytest
+
+LOSSLESS_STAGES = ("dc_quant", "acs", "raw_qf", "coeffs", "nzeros", "cmap", "quant_params")
+
+
+def roundtrip(oracle, img, distance=1.0, effort=7, proposal=0, flags=1):
+    f = oracle.encode(img, distance, effort, proposal, flags)
+    assert f.error == ""
+    cs = f.dump("codestream")
+    assert cs[0] == 0xFF and cs[1] == 0x0A
+    d = oracle.decode(cs.tobytes())
+    assert d.error == "", d.error
+    for st in LOSSLESS_STAGES:
+        a, b = f.dump(st), d.dump(st)
+        assert a.shape == b.shape and np.array_equal(a, b), st
+    assert int(d.dump("num_clusters")[0]) == int(f.dump("num_clusters")[0])
+    assert np.array_equal(d.dump("context_map"), f.dump("context_map"))
+    return f, cs
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (8, 8), (64, 64), (256, 256), (257, 9), (264, 300), (520, 260)])
+def test_roundtrip_sizes(pkg, oracle, w, h):
+    roundtrip(oracle, pkg.synth_image(w, h, w + 3 * h))
+
+
+@pytest.mark.parametrize("distance", [0.5, 1.0, 3.0, 8.0, 14.0])
+def test_roundtrip_distances(pkg, oracle, distance):
+    f, cs = roundtrip(oracle, pkg.synth_image(320, 200, 7), distance)
+
+
+def test_roundtrip_extremes(pkg, oracle):
+    for fill in (0, 255):
+        roundtrip(oracle, np.full((40, 72, 3), fill, dtype=np.uint8))
+    rng = np.random.default_rng(3)
+    roundtrip(oracle, rng.integers(0, 256, size=(72, 96, 3), dtype=np.uint8))
+    roundtrip(oracle, rng.integers(0, 256, size=(300, 280, 3), dtype=np.uint8), distance=0.1)
+
+
+def test_bpp_decreases_with_distance(pkg, oracle):
+    img = pkg.synth_image(512, 384, 21)
+    sizes = [oracle.encode(img, d, 7, 0, 1).dump("codestream").size for d in (0.5, 1.0, 2.0, 4.0, 8.0)]
+    assert all(a > b for a, b in zip(sizes, sizes[1:])), sizes
+
+
+def test_token_stream_layout(pkg, oracle):
+    img = pkg.synth_image(600, 300, 5)
+    f = oracle.encode(img, 1.0, 7, 0, 1)
+    d = oracle.dims(600, 300)
+    off = f.dump("token_offsets")
+    tok = f.dump("tokens")
+    assert off.size == d["num_groups"] + 1 and off[0] == 0 and off[-1] == tok.size
+    assert (tok >> 16).max() < 7425
+    hist = f.dump("histograms").reshape(7425, 64)
+    assert hist.sum() == tok.size
+    goff = f.dump("group_offsets")
+    assert goff[-1] == f.dump("group_streams").size
+
+
+def test_corrupt_stream_rejected(pkg, oracle):
+    img = pkg.synth_image(300, 280, 9)
+    cs = oracle.encode(img, 1.0, 7, 0, 1).dump("codestream").copy()
+    assert oracle.decode(cs[:-7].tobytes()).error != ""
+    bad = cs.copy(); bad[0] = 0
+    assert oracle.decode(bad.tobytes()).error != ""
+    flips = 0
+    for pos in range(60, cs.size, max(1, cs.size // 40)):
+        bad = cs.copy(); bad[pos] ^= 0x10
+        d = oracle.decode(bad.tobytes())
+        if d.error != "" or not np.array_equal(d.dump("coeffs"), oracle.decode(cs.tobytes()).dump("coeffs")) \
+                or not np.array_equal(d.dump("dc_quant"), oracle.decode(cs.tobytes()).dump("dc_quant")):
+            flips += 1
+    assert flips >= 30   # nearly every bit flip is either rejected or changes the decoded integers

@@ -5,10 +5,12 @@
 #include "encoder.h"
 #include "host_tables.h"
 #include "kernels.h"
+#include "entropy.cuh"
 
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace jxlb {
 
@@ -47,6 +49,24 @@ bool Encoder::Init(int device, std::string* err) {
     if (!d_izz8_.Reserve(64)) { *err = "alloc"; return false; }
     CUDA_OK(cudaMemcpy(d_izz8_.p, izz, 64, cudaMemcpyHostToDevice));
   }
+  {
+    // Q20 log2 table of the clustering cost (same expression as the oracle's Log2Q20)
+    std::vector<int> lut(1025);
+    for (int i = 0; i <= 1024; ++i) lut[i] = (int)lrint(ldexp(log2(1.0 + (double)i / 1024.0), 20));
+    if (!d_log2lut_.Reserve(1025)) { *err = "alloc"; return false; }
+    CUDA_OK(cudaMemcpy(d_log2lut_.p, lut.data(), 1025 * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  if (!(d_hist_.Reserve((size_t)kNumAcContexts * kAcAlphabet) && d_cluster_hist_.Reserve(kMaxClusters * kAcAlphabet) &&
+        d_hdr_bits_.Reserve(kMaxClusters * 64) && d_hdr_len_.Reserve(kMaxClusters) &&
+        d_cluster_state_.Reserve(cluster_state_bytes()) && d_ctx_map_.Reserve(kNumAcContexts + 64) &&
+        d_info_.Reserve((size_t)kMaxClusters * kAcAlphabet * 8) && d_norm_.Reserve(kMaxClusters * kAcAlphabet) &&
+        d_rmap_.Reserve((size_t)kMaxClusters * kAnsTabSize) && d_mod_hist_.Reserve(kNumModularCtx * kModAlphabet) &&
+        d_lf_words_.Reserve(4096) && d_small_.Reserve(16) && d_tree_words_.Reserve(256) &&
+        d_code_len_.Reserve(kNumModularCtx * kModAlphabet) && d_code_bits_.Reserve(kNumModularCtx * kModAlphabet) &&
+        d_cm_back_.Reserve(8192) && d_hf_words_.Reserve(8192 + kMaxClusters * 64 + 256) && d_out_info_.Reserve(2))) {
+    *err = "alloc"; return false;
+  }
+  CUDA_OK(cudaMallocHost(&h_out_info_, 2 * sizeof(unsigned long long)));
   if (!d_cvx_.Reserve(27) || !d_cvy_.Reserve(27) || !d_q_.Reserve(1)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_cvx_.p, kCoveredX, 27, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d_cvy_.p, kCoveredY, 27, cudaMemcpyHostToDevice));
@@ -62,7 +82,16 @@ void Encoder::Destroy() {
   d_izz8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   d_rgb_.Release(); d_xyb_.Release(); d_mask1x1_.Release(); d_pre_.Release(); d_qf_.Release(); d_mask_.Release();
   d_homog_.Release(); d_acs_entropy_.Release(); d_acs_.Release(); d_raw_qf_.Release(); d_cmap_.Release();
-  d_coeffs_.Release(); d_dc_quant_.Release(); d_nzeros_.Release(); d_lastpos_.Release(); d_q_.Release();
+  d_coeffs_.Release(); d_dc_quant_.Release(); d_nzeros_.Release(); d_nzcount_.Release(); d_lastk_.Release(); d_q_.Release();
+  d_log2lut_.Release(); d_tokens_.Release(); d_token_counts_.Release(); d_hist_.Release(); d_cluster_hist_.Release();
+  d_hdr_bits_.Release(); d_hdr_len_.Release(); d_group_arena_.Release(); d_cluster_state_.Release(); d_ctx_map_.Release();
+  d_info_.Release(); d_norm_.Release(); d_rmap_.Release(); d_group_start_.Release(); d_dgs_.Release(); d_strat_c_.Release();
+  d_qf_c_.Release(); d_first_count_.Release(); d_mod_tokens_.Release(); d_mod_hist_.Release(); d_lf_words_.Release();
+  d_small_.Release(); d_tile_sums_.Release(); d_mod_words_.Release(); d_dg_start_.Release(); d_tree_words_.Release();
+  d_code_len_.Release(); d_code_bits_.Release(); d_cm_back_.Release(); d_hf_words_.Release(); d_hdr_stage_.Release();
+  d_out_.Release(); d_sections_.Release(); d_out_info_.Release();
+  if (h_out_info_) cudaFreeHost(h_out_info_);
+  h_out_info_ = nullptr;
   if (h_pinned_) cudaFreeHost(h_pinned_);
   h_pinned_ = nullptr;
   for (auto& e : ev_) if (e) cudaEventDestroy(e);
@@ -78,7 +107,30 @@ bool Encoder::Reserve(const FrameDim& fd, std::string* err) {
             d_acs_entropy_.Reserve(nblk) && d_acs_.Reserve(nblk) && d_raw_qf_.Reserve(nblk) &&
             d_cmap_.Reserve((size_t)2 * fd.txs * fd.tys) &&
             d_coeffs_.Reserve((size_t)fd.num_groups * kGroupBlocks * 192) && d_dc_quant_.Reserve(3 * nblk) &&
-            d_nzeros_.Reserve(3 * nblk) && d_lastpos_.Reserve(3 * nblk);
+            d_nzeros_.Reserve(3 * nblk) && d_nzcount_.Reserve(3 * nblk) && d_lastk_.Reserve(3 * nblk);
+  // modular element space: one fixed-capacity run per DC group (k_modular.cu)
+  h_dgs_.clear();
+  uint32_t elem = 0, blocks = 0;
+  for (int dg = 0; dg < fd.num_dc_groups; ++dg) {
+    DcGroupInfo d;
+    d.x0 = (dg % fd.dgxs) * 256; d.y0 = (dg / fd.dgxs) * 256;
+    d.w = std::min(256, fd.bxs - d.x0); d.h = std::min(256, fd.bys - d.y0);
+    d.tw = (d.w + 7) >> 3; d.th = (d.h + 7) >> 3;
+    d.elem_base = elem; d.block_base = blocks;
+    elem += 2 + 6 * (uint32_t)(d.w * d.h) + 2 * (uint32_t)(d.tw * d.th);
+    blocks += (uint32_t)(d.w * d.h);
+    h_dgs_.push_back(d);
+  }
+  total_elems_ = elem;
+  const size_t nsec = (size_t)2 + fd.num_dc_groups + fd.num_groups;
+  const size_t out_words = ((size_t)fd.xsize * fd.ysize * 4 + (1u << 20) + nsec * 8) / 4;
+  ok = ok && d_tokens_.Reserve((size_t)fd.num_groups * kTokensPerGroupMax) && d_token_counts_.Reserve(fd.num_groups) &&
+       d_group_arena_.Reserve((size_t)fd.num_groups * kTokensPerGroupMax) && d_group_start_.Reserve(fd.num_groups) &&
+       d_dgs_.Reserve(fd.num_dc_groups) && d_strat_c_.Reserve(nblk) && d_qf_c_.Reserve(nblk) &&
+       d_first_count_.Reserve(fd.num_dc_groups) && d_mod_tokens_.Reserve(total_elems_) &&
+       d_tile_sums_.Reserve(total_elems_ / 2048 + 2) && d_mod_words_.Reserve((size_t)total_elems_ + 2) &&
+       d_dg_start_.Reserve(fd.num_dc_groups) && d_hdr_stage_.Reserve(nsec + 64) && d_sections_.Reserve(nsec) &&
+       d_out_.Reserve(out_words);
   if (!ok) { *err = "device allocation failed"; return false; }
   return true;
 }
@@ -158,10 +210,55 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
   // K7: transform + quantise
   launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
                     b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
-                    d_lastpos_.p, stream_);
+                    d_nzcount_.p, d_lastk_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
+  // K8: tokens + per-context histograms
+  CUDA_OK(cudaMemsetAsync(d_hist_.p, 0, (size_t)kNumAcContexts * kAcAlphabet * 4, stream_));
+  CUDA_OK(cudaMemsetAsync(d_cluster_hist_.p, 0, kMaxClusters * kAcAlphabet * 4, stream_));
+  launch_tokenize(d_acs_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p, d_coeffs_.p, fd, d_tokens_.p, d_token_counts_.p,
+                  d_hist_.p, stream_);
+  CUDA_OK(cudaEventRecord(ev_[7], stream_));
+  // K9: clustering, per-cluster ANS tables
+  launch_cluster(d_hist_.p, d_log2lut_.p, d_cluster_state_.p, d_ctx_map_.p, d_cluster_hist_.p, stream_);
+  launch_ans_tables(d_cluster_hist_.p, d_cluster_state_.p, d_norm_.p, d_rmap_.p, d_info_.p, d_hdr_bits_.p, d_hdr_len_.p,
+                    stream_);
+  CUDA_OK(cudaEventRecord(ev_[8], stream_));
+  // K10: one rANS stream per AC group
+  launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_group_arena_.p, d_group_start_.p,
+                    fd.num_groups, stream_);
+  CUDA_OK(cudaEventRecord(ev_[9], stream_));
+  // K11: modular DC + AC metadata streams, LfGlobal
+  uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;
+  uint32_t* tree_bits = d_small_.p + 3;
+  if (tree_ndc_ != fd.num_dc_groups) {
+    launch_tree_blob(fd.num_dc_groups, d_tree_words_.p, tree_bits, stream_);
+    tree_ndc_ = fd.num_dc_groups;
+  }
+  CUDA_OK(cudaMemcpyAsync(d_dgs_.p, h_dgs_.data(), h_dgs_.size() * sizeof(DcGroupInfo), cudaMemcpyHostToDevice, stream_));
+  CUDA_OK(cudaMemsetAsync(d_mod_hist_.p, 0, kNumModularCtx * kModAlphabet * 4, stream_));
+  CUDA_OK(cudaMemsetAsync(d_mod_words_.p, 0, ((size_t)total_elems_ + 2) * 4, stream_));
+  launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, stream_);
+  launch_mod_tokens(d_dc_quant_.p, d_cmap_.p, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, fd, d_dgs_.p, fd.num_dc_groups,
+                    total_elems_, d_mod_tokens_.p, d_mod_hist_.p, stream_);
+  launch_mod_codes(d_mod_hist_.p, d_q_.p, d_tree_words_.p, tree_bits, d_code_len_.p, d_code_bits_.p, d_lf_words_.p, lf_bits,
+                   stream_);
+  launch_mod_write(d_mod_tokens_.p, d_code_len_.p, d_code_bits_.p, d_dgs_.p, fd.num_dc_groups, d_first_count_.p, total_elems_,
+                   d_tile_sums_.p, mod_total_bits, d_mod_words_.p, d_dg_start_.p, stream_);
+  CUDA_OK(cudaEventRecord(ev_[10], stream_));
+  // K12: HfGlobal, headers + TOC, concatenation
+  const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
+  launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
+                   hf_bits, stream_);
+  launch_finalize(fd, x_qm_scale_, b_qm_scale_, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,
+                  d_sections_.p, d_hdr_stage_.p, d_out_.p, (unsigned long long)d_out_.cap * 32, d_out_info_.p, stream_);
+  launch_assemble(d_sections_.p, 2 + fd.num_dc_groups + fd.num_groups, d_lf_words_.p, d_mod_words_.p, d_hf_words_.p,
+                  d_group_arena_.p, d_out_.p, d_out_info_.p, stream_);
+  CUDA_OK(cudaEventRecord(ev_[11], stream_));
+  CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
+  if (h_out_info_[1]) { *err = "codestream larger than the output arena"; return false; }
+  codestream_bytes_ = (size_t)h_out_info_[0];
   have_frame_ = true;
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -178,15 +275,36 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
     cudaEventElapsedTime(&ms, ev_[3], ev_[4]); stats->stage_ms[JXLB200_T_HOMOG] = ms;
     cudaEventElapsedTime(&ms, ev_[4], ev_[5]); stats->stage_ms[JXLB200_T_ACS] = ms;
     cudaEventElapsedTime(&ms, ev_[5], ev_[6]); stats->stage_ms[JXLB200_T_COEFF] = ms;
-    cudaEventElapsedTime(&ms, ev_[0], ev_[6]); stats->total_ms = ms;
+    cudaEventElapsedTime(&ms, ev_[6], ev_[7]); stats->stage_ms[JXLB200_T_TOKENIZE] = ms;
+    cudaEventElapsedTime(&ms, ev_[7], ev_[8]); stats->stage_ms[JXLB200_T_HISTO] = ms;
+    cudaEventElapsedTime(&ms, ev_[8], ev_[9]); stats->stage_ms[JXLB200_T_ANS] = ms;
+    cudaEventElapsedTime(&ms, ev_[9], ev_[10]); stats->stage_ms[JXLB200_T_DC] = ms;
+    cudaEventElapsedTime(&ms, ev_[10], ev_[11]); stats->stage_ms[JXLB200_T_ASSEMBLE] = ms;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[11]); stats->total_ms = ms;
+    stats->codestream_bytes = codestream_bytes_;
+    stats->bpp = 8.0 * (double)codestream_bytes_ / ((double)fd.xsize * fd.ysize);
+    {
+      std::vector<uint32_t> counts(fd.num_groups);
+      CUDA_OK(cudaMemcpy(counts.data(), d_token_counts_.p, counts.size() * 4, cudaMemcpyDeviceToHost));
+      uint64_t nt = 0;
+      for (uint32_t c : counts) nt += c;
+      stats->num_tokens = nt;
+      int k = 0;
+      CUDA_OK(cudaMemcpy(&k, d_cluster_state_.p + cluster_num_clusters_offset(), 4, cudaMemcpyDeviceToHost));
+      stats->num_clusters = (uint32_t)k;
+    }
   }
   return true;
 }
 
 bool Encoder::Fetch(uint8_t** out, size_t* out_len, std::string* err) {
   if (!have_frame_) { *err = "no encoded frame"; return false; }
-  *out = (uint8_t*)malloc(1);
-  *out_len = 0;
+  cudaSetDevice(device_);
+  uint8_t* buf = (uint8_t*)malloc(codestream_bytes_ ? codestream_bytes_ : 1);
+  if (!buf) { *err = "out of host memory"; return false; }
+  if (cudaMemcpy(buf, d_out_.p, codestream_bytes_, cudaMemcpyDeviceToHost) != cudaSuccess) { free(buf); *err = "memcpy"; return false; }
+  *out = buf;
+  *out_len = codestream_bytes_;
   return true;
 }
 
@@ -211,6 +329,28 @@ int64_t Encoder::Dump(int stage, void* dst, size_t cap, std::string* err) {
     case JXLB200_STAGE_COEFFS: src = d_coeffs_.p; bytes = (size_t)fd.num_groups * kGroupBlocks * 192 * 2; break;
     case JXLB200_STAGE_DC_QUANT: src = d_dc_quant_.p; bytes = 3 * nblk * 2; break;
     case JXLB200_STAGE_NZEROS: src = d_nzeros_.p; bytes = 3 * nblk; break;
+    case JXLB200_STAGE_HISTOGRAMS: src = d_hist_.p; bytes = (size_t)kNumAcContexts * kAcAlphabet * 4; break;
+    case JXLB200_STAGE_CONTEXT_MAP: src = d_ctx_map_.p; bytes = kNumAcContexts; break;
+    case JXLB200_STAGE_CODESTREAM: src = d_out_.p; bytes = codestream_bytes_; break;
+    case 21: src = d_cluster_state_.p + cluster_num_clusters_offset(); bytes = 4; break;
+    case JXLB200_STAGE_TOKEN_OFFSETS:
+    case JXLB200_STAGE_TOKENS: {
+      std::vector<uint32_t> counts(fd.num_groups), offs(fd.num_groups + 1, 0);
+      if (cudaMemcpy(counts.data(), d_token_counts_.p, counts.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }
+      for (int g = 0; g < fd.num_groups; ++g) offs[g + 1] = offs[g] + counts[g];
+      if (stage == JXLB200_STAGE_TOKEN_OFFSETS) {
+        bytes = offs.size() * 4;
+        if (dst && cap >= bytes) memcpy(dst, offs.data(), bytes);
+        return (int64_t)bytes;
+      }
+      bytes = (size_t)offs.back() * 4;
+      if (dst && cap >= bytes) {
+        for (int g = 0; g < fd.num_groups; ++g)
+          if (counts[g] && cudaMemcpy((uint8_t*)dst + (size_t)offs[g] * 4, d_tokens_.p + (size_t)g * kTokensPerGroupMax,
+                                      (size_t)counts[g] * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }
+      }
+      return (int64_t)bytes;
+    }
     case JXLB200_STAGE_QUANT_PARAMS: {
       QuantDev q;
       if (cudaMemcpy(&q, d_q_.p, sizeof(q), cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }

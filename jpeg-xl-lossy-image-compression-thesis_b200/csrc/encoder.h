@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/jxlb200.h"
 #include "jxl_common.cuh"
+#include "kernels.h"
 #include <string>
 #include <vector>
 
@@ -65,8 +66,33 @@ class Encoder {
   DevBuf<int32_t> d_raw_qf_;
   DevBuf<int8_t> d_cmap_;
   DevBuf<int16_t> d_coeffs_, d_dc_quant_;
-  DevBuf<uint8_t> d_nzeros_, d_lastpos_;
+  DevBuf<uint8_t> d_nzeros_;
+  DevBuf<uint16_t> d_nzcount_, d_lastk_;
   DevBuf<QuantDev> d_q_;
+  // entropy stage: AC tokens / histograms / clusters / ANS tables / group streams
+  DevBuf<int> d_log2lut_;
+  DevBuf<uint32_t> d_tokens_, d_token_counts_, d_hist_, d_cluster_hist_, d_hdr_bits_, d_hdr_len_, d_group_arena_;
+  DevBuf<uint8_t> d_cluster_state_, d_ctx_map_, d_info_;
+  DevBuf<uint16_t> d_norm_, d_rmap_;
+  DevBuf<unsigned long long> d_group_start_;
+  // modular streams (DC + AC metadata)
+  std::vector<DcGroupInfo> h_dgs_;
+  uint32_t total_elems_ = 0;
+  int tree_ndc_ = -1;
+  DevBuf<DcGroupInfo> d_dgs_;
+  DevBuf<int32_t> d_strat_c_, d_qf_c_;
+  DevBuf<uint32_t> d_first_count_, d_mod_tokens_, d_mod_hist_, d_lf_words_, d_small_, d_tile_sums_, d_mod_words_, d_dg_start_,
+      d_tree_words_;
+  DevBuf<uint8_t> d_code_len_;
+  DevBuf<uint16_t> d_code_bits_;
+  // frame assembly
+  DevBuf<uint32_t> d_cm_back_, d_hf_words_, d_hdr_stage_, d_out_;
+  DevBuf<Section> d_sections_;
+  DevBuf<unsigned long long> d_out_info_;
+  unsigned long long* h_out_info_ = nullptr;   // pinned
+  size_t codestream_bytes_ = 0;
+  int num_clusters_ = 0;
+  uint64_t num_tokens_ = 0;
 };
 
 }  // namespace jxlb

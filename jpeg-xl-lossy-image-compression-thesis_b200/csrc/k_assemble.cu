@@ -1,0 +1,232 @@
+// K12 — frame assembly on the device (stage U9): HfGlobal (context map + cluster histograms),
+// codestream / frame headers, TOC and the concatenation of every section into the output
+// buffer.  Field orders follow libjxl headers.cc, frame_header.cc, enc_toc.cc, enc_frame.cc,
+// enc_context_map.cc [UPSTREAM]; encoder choices are listed in DESIGN.md "Bitstream".
+#include "entropy.cuh"
+#include "kernels.h"
+
+namespace jxlb {
+
+// ---- HfGlobal: context map (ANS coded, no MTF) + the per-cluster uint configs and histograms
+__global__ void __launch_bounds__(256) k_hf_global(const uint8_t* __restrict__ cmap, const int* __restrict__ num_clusters_p,
+                                                   const uint32_t* __restrict__ hdr_bits, const uint32_t* __restrict__ hdr_len,
+                                                   int num_groups, uint32_t* __restrict__ cm_back, uint32_t* __restrict__ hf_words,
+                                                   uint32_t* __restrict__ hf_bits) {
+  __shared__ uint32_t s_hist[kAcAlphabet];
+  __shared__ uint16_t s_norm[kAcAlphabet];
+  __shared__ uint16_t s_scratch[1024];
+  __shared__ uint16_t s_rmap[kAnsTabSize];
+  __shared__ AnsSymInfo s_info[kAcAlphabet];
+  __shared__ long long s_start;
+  constexpr int kBackWords = 8192;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int K = *num_clusters_p;
+  if (t < kAcAlphabet) s_hist[t] = 0;
+  __syncthreads();
+  if (K > 1) {
+    for (int i = t; i < kNumAcContexts; i += 256) {
+      uint32_t tk, nb, bits;
+      hybrid_encode(cmap[i], tk, nb, bits);
+      atomicAdd(&s_hist[tk], 1u);
+    }
+    __syncthreads();
+    if (t == 0) normalize_counts(s_hist, kAcAlphabet, s_norm);
+    __syncthreads();
+    if (warp == 0) {
+      build_reverse_map(s_norm, kAcAlphabet, s_scratch, s_rmap, s_info, lane);
+      BackWriterDev bw;
+      bw.init(cm_back, kBackWords);
+      uint32_t state = kAnsInitState;
+      for (int hi = kNumAcContexts; hi > 0; hi -= 32) {
+        const int i = hi - 1 - lane;
+        uint32_t freq = 0, rcp = 0, rbase = 0, xb = 0;
+        if (i >= 0) {
+          uint32_t tk, nb, bits;
+          hybrid_encode(cmap[i], tk, nb, bits);
+          freq = s_info[tk].freq; rcp = s_info[tk].rcp; rbase = s_info[tk].base; xb = (nb << 16) | bits;
+        }
+        const int m = min(32, hi);
+        for (int j = 0; j < m; ++j) {
+          const uint32_t f = __shfl_sync(0xffffffffu, freq, j);
+          const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
+          const uint32_t rb = __shfl_sync(0xffffffffu, rbase, j);
+          const uint32_t x = __shfl_sync(0xffffffffu, xb, j);
+          bw.push((int)(x >> 16), x & 0xFFFF, lane == 0);
+          uint32_t o16;
+          if (ans_put(state, f, rc, s_rmap + rb, o16)) bw.push(16, o16, lane == 0);
+        }
+      }
+      bw.push(32, state, lane == 0);
+      const long long sb = bw.finish(lane == 0);
+      if (lane == 0) s_start = sb;
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    BitWriterDev w;
+    w.init(hf_words);
+    w.write(1, 1);                                                  // default dequant matrices
+    const int lg = num_groups <= 1 ? 0 : 32 - __clz(num_groups - 1);
+    w.write(lg, 0);                                                 // num_histograms - 1
+    w.write(2, 2);                                                  // used_orders = 0
+    w.write(1, 0);                                                  // lz77 disabled
+    if (K == 1) { w.write(1, 1); w.write(2, 0); }
+    else {
+      w.write(1, 0); w.write(1, 0);                                 // not simple, no MTF
+      w.write(1, 0); w.write(1, 0); w.write(2, kLogAlphaSize - 5);  // nested code: no lz77, ANS, alphabet 2^8
+      w.write(4, 4); w.write(3, 2); w.write(2, 0);
+      write_ans_histogram(s_norm, kAcAlphabet, w);
+      const long long sb = s_start;
+      for (long long p = sb; p < (long long)kBackWords * 32;) {
+        const int n = (int)min((long long)(32 - (p & 31)), (long long)kBackWords * 32 - p);
+        w.write(n, (cm_back[p >> 5] >> (p & 31)) & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1)));
+        p += n;
+      }
+    }
+    w.write(1, 0);                                                  // ANS
+    w.write(2, kLogAlphaSize - 5);
+    for (int k = 0; k < K; ++k) { w.write(4, 4); w.write(3, 2); w.write(2, 0); }
+    for (int k = 0; k < K; ++k) w.append(hdr_bits + (size_t)k * 64, hdr_len[k]);
+    w.flush();
+    *hf_bits = w.bits();
+  }
+}
+
+// ---- headers + TOC + section placement
+__device__ void write_size_u32(BitWriterDev& w, uint32_t v) {
+  const uint32_t m = v - 1;
+  if (m < (1u << 9)) { w.write(2, 0); w.write(9, m); }
+  else if (m < (1u << 13)) { w.write(2, 1); w.write(13, m); }
+  else if (m < (1u << 18)) { w.write(2, 2); w.write(18, m); }
+  else { w.write(2, 3); w.write(30, m); }
+}
+
+__global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, int b_qm_scale, const uint32_t* __restrict__ lf_bits,
+                                                 const uint32_t* __restrict__ dg_start_bit, const uint32_t* __restrict__ mod_total_bits,
+                                                 const uint32_t* __restrict__ hf_bits, const unsigned long long* __restrict__ group_start_bit,
+                                                 Section* __restrict__ sections, uint32_t* __restrict__ hdr_stage,
+                                                 uint32_t* __restrict__ out_words, unsigned long long out_capacity_bits,
+                                                 unsigned long long* __restrict__ out_info) {
+  if (threadIdx.x != 0) return;
+  const int ndc = fd.num_dc_groups, ng = fd.num_groups;
+  const bool small = ng == 1;
+  const int nsec = 2 + ndc + ng;
+  // section sources and lengths
+  for (int i = 0; i < nsec; ++i) {
+    Section s;
+    if (i == 0) { s.kind = 0; s.index = 0; s.src_bit = 0; s.nbits = *lf_bits; }
+    else if (i <= ndc) {
+      const int dg = i - 1;
+      const unsigned long long b0 = dg_start_bit[dg], b1 = dg + 1 < ndc ? dg_start_bit[dg + 1] : *mod_total_bits;
+      s.kind = 1; s.index = dg; s.src_bit = b0; s.nbits = b1 - b0;
+    } else if (i == ndc + 1) { s.kind = 2; s.index = 0; s.src_bit = 0; s.nbits = *hf_bits; }
+    else {
+      const int g = i - ndc - 2;
+      s.kind = 3; s.index = g; s.src_bit = group_start_bit[g]; s.nbits = (unsigned long long)kTokensPerGroupMax * 32 - s.src_bit;
+    }
+    s.dst_bit = 0;
+    sections[i] = s;
+  }
+  // codestream headers, frame header and TOC into the staging words
+  BitWriterDev w;
+  w.init(hdr_stage);
+  w.write(8, 0xFF); w.write(8, 0x0A);
+  w.write(1, 0);                                  // SizeHeader: not small
+  write_size_u32(w, (uint32_t)fd.ysize);
+  w.write(3, 0);                                  // ratio 0: explicit xsize
+  write_size_u32(w, (uint32_t)fd.xsize);
+  w.write(1, 1); w.write(1, 1);                   // ImageMetadata.all_default, default_m
+  if (w.bits() & 7) w.write(8 - (int)(w.bits() & 7), 0);
+  w.write(1, 0); w.write(2, 0); w.write(1, 0);    // frame header: not all_default, regular frame, VarDCT
+  w.write(2, 2); w.write(8, 128 - 17);            // flags = kSkipAdaptiveDCSmoothing (U64 selector 2)
+  w.write(2, 0);                                  // upsampling 1
+  w.write(3, (uint32_t)x_qm_scale); w.write(3, (uint32_t)b_qm_scale);
+  w.write(2, 0); w.write(1, 0); w.write(2, 0);    // one pass, no crop, blend replace
+  w.write(1, 1); w.write(2, 0);                   // is_last, no name
+  w.write(1, 0); w.write(1, 0); w.write(2, 0); w.write(2, 0);  // loop filter: gab off, epf 0, no extensions
+  w.write(2, 0);                                  // no frame-header extensions
+  w.write(1, 0);                                  // TOC not permuted
+  if (w.bits() & 7) w.write(8 - (int)(w.bits() & 7), 0);
+  unsigned long long total_small_bits = 0;
+  if (small) for (int i = 0; i < nsec; ++i) total_small_bits += sections[i].nbits;
+  const int ntoc = small ? 1 : nsec;
+  for (int i = 0; i < ntoc; ++i) {
+    const uint32_t size = (uint32_t)(((small ? total_small_bits : sections[i].nbits) + 7) >> 3);
+    if (size < 1024) { w.write(2, 0); w.write(10, size); }
+    else if (size < 17408) { w.write(2, 1); w.write(14, size - 1024); }
+    else if (size < 4211712) { w.write(2, 2); w.write(22, size - 17408); }
+    else { w.write(2, 3); w.write(30, size - 4211712); }
+  }
+  if (w.bits() & 7) w.write(8 - (int)(w.bits() & 7), 0);
+  w.flush();
+  const uint32_t header_bits = w.bits();
+  unsigned long long pos = header_bits;
+  for (int i = 0; i < nsec; ++i) {
+    sections[i].dst_bit = pos;
+    pos += small ? sections[i].nbits : ((sections[i].nbits + 7) & ~7ull);
+  }
+  pos = (pos + 7) & ~7ull;
+  const bool overflow = pos + 64 > out_capacity_bits;
+  out_info[0] = overflow ? 0 : pos >> 3;
+  out_info[1] = overflow ? 1 : 0;
+  if (overflow) return;
+  // the words a section covers only partially are ORed into by k_assemble: clear them first
+  for (int i = 0; i < nsec; ++i) {
+    const unsigned long long a = sections[i].dst_bit, b = a + sections[i].nbits;
+    out_words[a >> 5] = 0;
+    out_words[b >> 5] = 0;
+  }
+  out_words[pos >> 5] = 0;
+  for (uint32_t i = 0; i < (header_bits + 31) / 32; ++i) out_words[i] = hdr_stage[i];
+}
+
+__global__ void __launch_bounds__(256) k_assemble(const Section* __restrict__ sections, const uint32_t* __restrict__ lf_words,
+                                                  const uint32_t* __restrict__ mod_words, const uint32_t* __restrict__ hf_words,
+                                                  const uint32_t* __restrict__ group_arena, uint32_t* __restrict__ out_words,
+                                                  const unsigned long long* __restrict__ out_info) {
+  if (out_info[1]) return;
+  const Section s = sections[blockIdx.y];
+  if (s.nbits == 0) return;
+  const uint32_t* src = s.kind == 0 ? lf_words : (s.kind == 1 ? mod_words : (s.kind == 2 ? hf_words
+                                   : group_arena + (size_t)s.index * kTokensPerGroupMax));
+  const unsigned long long d0 = s.dst_bit, d1 = s.dst_bit + s.nbits;
+  const unsigned long long w0 = d0 >> 5, w1 = (d1 + 31) >> 5;
+  for (unsigned long long wi = w0 + blockIdx.x * 256 + threadIdx.x; wi < w1; wi += (unsigned long long)gridDim.x * 256) {
+    const unsigned long long lo = max(wi << 5, d0), hi = min((wi + 1) << 5, d1);
+    const int n = (int)(hi - lo);
+    const unsigned long long sp = s.src_bit + (lo - d0);
+    const uint32_t a = src[sp >> 5];
+    const int sh = (int)(sp & 31);
+    uint32_t v = a >> sh;
+    if (sh + n > 32) v |= src[(sp >> 5) + 1] << (32 - sh);
+    if (n < 32) v &= (1u << n) - 1;
+    v <<= (int)(lo & 31);
+    if (n == 32) out_words[wi] = v; else atomicOr(&out_words[wi], v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32_t* hdr_bits, const uint32_t* hdr_len,
+                      int num_groups, uint32_t* cm_back, uint32_t* hf_words, uint32_t* hf_bits, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_hf_global<<<1, 256, 0, s>>>(cmap, num_clusters, hdr_bits, hdr_len, num_groups, cm_back, hf_words, hf_bits);
+}
+
+void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
+                     const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
+                     Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
+                     unsigned long long* out_info, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_finalize<<<1, 32, 0, s>>>(fd, x_qm_scale, b_qm_scale, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
+                             sections, hdr_stage, out_words, out_capacity_bits, out_info);
+}
+
+void launch_assemble(const Section* sections, int num_sections, const uint32_t* lf_words, const uint32_t* mod_words,
+                     const uint32_t* hf_words, const uint32_t* group_arena, uint32_t* out_words,
+                     const unsigned long long* out_info, cudaStream_t s) {
+  ++g_kernel_launches;
+  dim3 grid(8, num_sections);
+  k_assemble<<<grid, 256, 0, s>>>(sections, lf_words, mod_words, hf_words, group_arena, out_words, out_info);
+}
+
+}  // namespace jxlb

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) k_dct8_quant(const float* __restrict__ X,
                                                     const int8_t* __restrict__ cmap, float x_qm_mul, float b_qm_mul,
                                                     int adjust, int32_t* __restrict__ raw_qf,
                                                     int16_t* __restrict__ coeffs, int16_t* __restrict__ dc_quant,
-                                                    uint8_t* __restrict__ nzeros, uint8_t* __restrict__ lastpos) {
+                                                    uint8_t* __restrict__ nzeros, uint16_t* __restrict__ nzcount,
+                                                    uint16_t* __restrict__ lastk) {
   __shared__ float s_w[3][8][9];
   __shared__ float s_dqy[8][9];
   __shared__ uint8_t s_izz[64];
@@ -224,7 +225,8 @@ __global__ void __launch_bounds__(256) k_dct8_quant(const float* __restrict__ X,
       last = tree8_imax(last);
       if (h == 0 && active) {
         nzeros[(size_t)ch * nblk + bi] = (uint8_t)nz;
-        lastpos[(size_t)ch * nblk + bi] = (uint8_t)last;
+        nzcount[(size_t)ch * nblk + bi] = (uint16_t)nz;
+        lastk[(size_t)ch * nblk + bi] = (uint16_t)last;
       }
     }
     // ---- DC (AddVarDCTDC) + side data on lane 0 --------------------------------------------
@@ -259,11 +261,11 @@ __global__ void __launch_bounds__(256) k_dct8_quant(const float* __restrict__ X,
 void launch_dct8_quant(const float* x, const float* y, const float* b, const FrameDim& fd, const QuantDev* qd,
                        const float* weights, const float* dequant_y, const uint8_t* izz, const int8_t* cmap,
                        float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                       uint8_t* nzeros, uint8_t* lastpos, cudaStream_t s) {
+                       uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s) {
   dim3 grid(fd.gxs, (fd.bys + kRowsPerCta - 1) / kRowsPerCta);
   ++g_kernel_launches;
   k_dct8_quant<<<grid, 256, 0, s>>>(x, y, b, fd, qd, weights, dequant_y, izz, cmap, x_qm_mul, b_qm_mul, adjust, raw_qf,
-                                    coeffs, dc_quant, nzeros, lastpos);
+                                    coeffs, dc_quant, nzeros, nzcount, lastk);
 }
 
 }  // namespace jxlb

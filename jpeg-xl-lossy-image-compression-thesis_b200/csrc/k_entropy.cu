@@ -1,0 +1,394 @@
+// K8-K10 — AC coefficient tokenisation + per-context histograms, histogram clustering,
+// per-cluster ANS tables, and the per-group reverse rANS encoder (stages U6-U8; libjxl
+// enc_entropy_coder.cc TokenizeCoefficients, ac_context.h, enc_cluster.cc, enc_ans.cc
+// [UPSTREAM]; algorithmic choices in DESIGN.md "Entropy stage").
+//
+//  k_tokenize    one CTA per 256x256 AC group: token counts per block-channel from
+//                (nzeros, last non-zero scan position), CTA-wide exclusive scan, then one warp per
+//                block-channel emits its tokens with ballot/popc for the running non-zero count;
+//                tokens leave as coalesced 32-bit stores, histogram bins by global REDs.
+//  k_cluster     ONE thread-block cluster of 8 CTAs: farthest-point seeding on an integer
+//                entropy distance; the per-round argmax travels through distributed shared
+//                memory (one cluster barrier per round instead of a grid-wide sync).
+//  k_ans_tables  one warp per cluster histogram: normalise to 4096, code the histogram header,
+//                build the alias table and the encoder's reverse map.
+//  k_ans_groups  one warp per AC group: tokens are fetched 32 at a time (coalesced), their
+//                cluster / symbol info is looked up in parallel, and the serial state chain
+//                runs over warp shuffles; bits are written backwards into the group's arena.
+#include "entropy.cuh"
+#include "kernels.h"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace jxlb {
+
+__constant__ uint8_t c_covered_x[27] = {1, 1, 1, 1, 2, 4, 1, 2, 1, 4, 2, 4, 1, 1, 1, 1, 1, 1, 8, 4, 8, 16, 8, 16, 32, 16, 32};
+__constant__ uint8_t c_covered_y[27] = {1, 1, 1, 1, 2, 4, 2, 1, 4, 1, 4, 2, 1, 1, 1, 1, 1, 1, 8, 8, 4, 16, 16, 8, 32, 32, 16};
+__constant__ uint8_t c_strategy_order[27] = {0, 1, 1, 1, 2, 3, 4, 4, 5, 5, 6, 6, 1, 1, 1, 1, 1, 1, 7, 8, 8, 9, 10, 10, 11, 12, 12};
+__constant__ uint8_t c_block_ctx_map[39] = {0, 1, 2, 2, 3, 3, 4, 5, 6, 6, 6, 6, 6, 7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14,
+                                            7, 8, 9, 9, 10, 11, 12, 13, 14, 14, 14, 14, 14};
+__constant__ uint8_t c_freq_ctx[64] = {0,  0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 15, 16, 16, 17, 17,
+                                       18, 18, 19, 19, 20, 20, 21, 21, 22, 22, 23, 23, 23, 23, 24, 24, 24, 24, 25, 25, 25, 25,
+                                       26, 26, 26, 26, 27, 27, 27, 27, 28, 28, 28, 28, 29, 29, 29, 29, 30, 30, 30, 30};
+__constant__ uint8_t c_nnz_ctx[64] = {0,   0,   31,  62,  62,  93,  93,  93,  93,  123, 123, 123, 123, 152, 152, 152,
+                                      152, 152, 152, 152, 152, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180, 180,
+                                      180, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206,
+                                      206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
+
+// ------------------------------------------------------------------------------------------ K8
+__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
+                                                  const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
+                                                  const int16_t* __restrict__ coeffs, FrameDim fd,
+                                                  uint32_t* __restrict__ tokens, uint32_t* __restrict__ token_counts,
+                                                  uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_off[3072 + 1];
+  __shared__ uint32_t s_warp[8];
+  const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int gx0 = (g % fd.gxs) * 32, gy0 = (g / fd.gxs) * 32;
+  const size_t nblk = (size_t)fd.bxs * fd.bys;
+  // ---- token count per (block, slot): 12 consecutive entries per thread = 4 blocks
+  uint32_t cnt[12];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int blk = t * 4 + i, lx = blk & 31, ly = blk >> 5;
+    const int bx = gx0 + lx, by = gy0 + ly;
+    const bool inside = bx < fd.bxs && by < fd.bys;
+    uint8_t a = 0;
+    if (inside) a = acs[(size_t)by * fd.bxs + bx];
+    const bool first = inside && (a & 0x80);
+    const int s = a & 0x7f;
+    const int n = first ? c_covered_x[s] * c_covered_y[s] : 1;
+#pragma unroll
+    for (int slot = 0; slot < 3; ++slot) {
+      const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
+      uint32_t v = 0;
+      if (first) {
+        const size_t bi = (size_t)c * nblk + (size_t)by * fd.bxs + bx;
+        const int nz = nzcount[bi];
+        v = 1 + (nz ? (uint32_t)(lastk[bi] - n + 1) : 0u);
+      }
+      cnt[i * 3 + slot] = v;
+      sum += v;
+    }
+  }
+  // CTA-wide exclusive scan of the per-thread sums
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t base = incl - sum;
+  for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { s_off[t * 12 + i] = base; base += cnt[i]; }
+  if (t == 255) { s_off[3072] = base; token_counts[g] = base; }
+  __syncthreads();
+  // ---- emit: one warp per (block, slot)
+  uint32_t* out = tokens + (size_t)g * kTokensPerGroupMax;
+  for (int e = warp; e < 3072; e += 8) {
+    const uint32_t off = s_off[e];
+    const uint32_t count = s_off[e + 1] - off;
+    if (count == 0) continue;
+    const int blk = e / 3, slot = e - blk * 3;
+    const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
+    const int lx = blk & 31, ly = blk >> 5, bx = gx0 + lx, by = gy0 + ly;
+    const int s = acs[(size_t)by * fd.bxs + bx] & 0x7f;
+    const int cx = c_covered_x[s], cy = c_covered_y[s], n = cx * cy, size = n * 64;
+    const int log2n = 31 - __clz(n);
+    const int block_ctx = c_block_ctx_map[(c < 2 ? c ^ 1 : 2) * kNumOrders + c_strategy_order[s]];
+    const uint8_t* nzp = nzeros + (size_t)c * nblk;
+    const size_t bi = (size_t)by * fd.bxs + bx;
+    int nz = nzcount[(size_t)c * nblk + bi];
+    if (lane == 0) {
+      int pred;
+      if (lx == 0) pred = ly == 0 ? 32 : nzp[bi - fd.bxs];
+      else if (ly == 0) pred = nzp[bi - 1];
+      else pred = (nzp[bi - fd.bxs] + nzp[bi - 1] + 1) >> 1;
+      const int p = pred >= 64 ? 64 : pred;
+      const int bucket = p < 8 ? p : 4 + (p >> 1);
+      const uint32_t ctx = (uint32_t)(bucket * kNumBlockCtx + block_ctx);
+      out[off] = (ctx << 16) | (uint32_t)nz;
+      uint32_t tok, nb, bits;
+      hybrid_encode((uint32_t)nz, tok, nb, bits);
+      atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+    }
+    if (count == 1) continue;
+    const int histo_offset = kNumBlockCtx * kNonZeroBuckets + kZeroDensityContextCount * block_ctx;
+    int prev_carry = nz > size / 16 ? 0 : 1;
+    const int last = n + (int)count - 2;  // scan position of the last non-zero coefficient
+    for (int k0 = n; k0 <= last; k0 += 32) {
+      const int k = k0 + lane;
+      int coef = 0;
+      if (k <= last) {
+        const int j = k >> 6;
+        const int jx = j % cx, jy = j / cx;
+        const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
+        coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, coef != 0);
+      const int nz_here = nz - __popc(mask & ((1u << lane) - 1));
+      const int prev = lane == 0 ? prev_carry : (int)((mask >> (lane - 1)) & 1);
+      if (k <= last) {
+        const int nzl = (nz_here + n - 1) >> log2n;
+        const uint32_t ctx = (uint32_t)(histo_offset + (c_nnz_ctx[nzl] + c_freq_ctx[k >> log2n]) * 2 + prev);
+        const uint32_t v = pack_signed(coef);
+        out[off + 1 + (k - n)] = (ctx << 16) | v;
+        uint32_t tok, nb, bits;
+        hybrid_encode(v, tok, nb, bits);
+        atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+      }
+      nz -= __popc(mask);
+      prev_carry = (int)(mask >> 31);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K9
+constexpr int kClusterCtas = 8;
+constexpr int kClusterThreads = 512;
+constexpr int kClusterWarps = kClusterCtas * kClusterThreads / 32;  // 128
+
+struct ClusterState {   // global scratch
+  long long dist[kNumAcContexts];
+  int assign[kNumAcContexts];
+  uint32_t total[kNumAcContexts];
+  int list[kNumAcContexts];
+  int list_len;
+  int num_clusters;
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// candidate ordering for the argmax: larger key first, lower context index on ties
+__device__ __forceinline__ bool better(long long ka, int ca, long long kb, int cb) { return ka > kb || (ka == kb && ca < cb); }
+
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
+    k_cluster(const uint32_t* __restrict__ hist, const int* __restrict__ lut_g, ClusterState* __restrict__ st,
+              uint8_t* __restrict__ cmap, uint32_t* __restrict__ cluster_hist, int max_clusters) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ int s_lut[1025];
+  __shared__ uint32_t s_hb[kAcAlphabet];
+  __shared__ long long s_xb[kAcAlphabet];
+  __shared__ long long s_cand_key[2][kClusterCtas];
+  __shared__ int s_cand_ctx[2][kClusterCtas];
+  __shared__ long long s_wkey[kClusterThreads / 32];
+  __shared__ int s_wctx[kClusterThreads / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int rank = (int)cluster.block_rank();
+  const int gwarp = rank * (kClusterThreads / 32) + warp;
+  for (int i = t; i < 1025; i += kClusterThreads) s_lut[i] = lut_g[i];
+  if (rank == 0 && t == 0) st->list_len = 0;
+  __syncthreads();
+  cluster.sync();
+  // ---- phase A: totals, list of non-empty contexts, first seed = largest total
+  long long best_key = -1; int best_ctx = 0x7fffffff;
+  for (int c = gwarp; c < kNumAcContexts; c += kClusterWarps) {
+    const uint32_t* h = hist + (size_t)c * kAcAlphabet;
+    uint32_t v = h[lane] + h[lane + 32];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) {
+      st->total[c] = v;
+      st->dist[c] = v ? 0x7fffffffffffffffll : -1;
+      st->assign[c] = 0;
+      if (v) { st->list[atomicAdd(&st->list_len, 1)] = c; }
+    }
+    if (v && better((long long)v, c, best_key, best_ctx)) { best_key = (long long)v; best_ctx = c; }
+  }
+  int K = 0;
+  int parity = 0;
+  for (;;) {
+    // ---- cluster-wide argmax of (best_key, best_ctx) over all warps
+    if (lane == 0) { s_wkey[warp] = best_key; s_wctx[warp] = best_ctx; }
+    __syncthreads();
+    if (t == 0) {
+      long long k = s_wkey[0]; int c = s_wctx[0];
+      for (int w = 1; w < kClusterThreads / 32; ++w) if (better(s_wkey[w], s_wctx[w], k, c)) { k = s_wkey[w]; c = s_wctx[w]; }
+      for (int r = 0; r < kClusterCtas; ++r) {
+        long long* rk = cluster.map_shared_rank(&s_cand_key[parity][0], r);
+        int* rc = cluster.map_shared_rank(&s_cand_ctx[parity][0], r);
+        rk[rank] = k; rc[rank] = c;
+      }
+    }
+    cluster.sync();
+    long long sk = s_cand_key[parity][0]; int seed = s_cand_ctx[parity][0];
+    for (int r = 1; r < kClusterCtas; ++r)
+      if (better(s_cand_key[parity][r], s_cand_ctx[parity][r], sk, seed)) { sk = s_cand_key[parity][r]; seed = s_cand_ctx[parity][r]; }
+    parity ^= 1;
+    if (sk < 0) break;                                        // no non-empty context at all
+    if (K > 0 && sk < ((long long)64 << 20)) break;           // nothing far enough from every seed
+    const int k = K++;
+    // ---- distances to the new seed
+    if (t < kAcAlphabet) {
+      const uint32_t b = hist[(size_t)seed * kAcAlphabet + t];
+      s_hb[t] = b;
+      s_xb[t] = xlogx(b, s_lut);
+    }
+    __syncthreads();
+    const uint32_t tb = st->total[seed];
+    const long long xtb = xlogx(tb, s_lut);
+    best_key = -1; best_ctx = 0x7fffffff;
+    const int n_list = st->list_len;
+    for (int i = gwarp; i < n_list; i += kClusterWarps) {
+      const int c = st->list[i];
+      const uint32_t* h = hist + (size_t)c * kAcAlphabet;
+      long long acc = 0;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int s = lane + 32 * half;
+        const uint32_t a = h[s], b = s_hb[s];
+        if (a && b) acc += xlogx(a + b, s_lut) - xlogx(a, s_lut) - s_xb[s];
+      }
+      acc = warp_sum_ll(acc);
+      const uint32_t ta = st->total[c];
+      long long d = xlogx(ta + tb, s_lut) - xlogx(ta, s_lut) - xtb - acc;
+      if (c == seed) d = 0;
+      long long cur = st->dist[c];
+      if (d < cur) {
+        cur = d;
+        if (lane == 0) { st->dist[c] = d; st->assign[c] = k; }
+      }
+      if (better(cur, c, best_key, best_ctx)) { best_key = cur; best_ctx = c; }
+    }
+    __syncthreads();  // s_hb / s_xb are rewritten next round
+    if (K >= max_clusters) break;
+  }
+  if (K == 0) K = 1;
+  cluster.sync();
+  // ---- cluster histograms (sum of members) and the context map
+  {
+    const int n_list = st->list_len;
+    for (int i = gwarp; i < n_list; i += kClusterWarps) {
+      const int c = st->list[i];
+      const int k = st->assign[c];
+      const uint32_t* h = hist + (size_t)c * kAcAlphabet;
+      for (int s = lane; s < kAcAlphabet; s += 32) { const uint32_t v = h[s]; if (v) atomicAdd(&cluster_hist[k * kAcAlphabet + s], v); }
+    }
+  }
+  if (rank == 0) {
+    // empty contexts inherit the cluster of the previous non-empty context (0 before the first)
+    __shared__ int s_carry[kClusterThreads];
+    constexpr int kChunk = (kNumAcContexts + kClusterThreads - 1) / kClusterThreads;
+    const int c0 = t * kChunk, c1 = min(c0 + kChunk, kNumAcContexts);
+    int lastv = -1;
+    for (int c = c0; c < c1; ++c) if (st->total[c]) lastv = st->assign[c];
+    s_carry[t] = lastv;
+    __syncthreads();
+    if (t == 0) {
+      int run = 0;
+      for (int i = 0; i < kClusterThreads; ++i) { const int v = s_carry[i]; s_carry[i] = run; if (v >= 0) run = v; }
+      st->num_clusters = K;
+    }
+    __syncthreads();
+    int prev = s_carry[t];
+    for (int c = c0; c < c1; ++c) { if (st->total[c]) prev = st->assign[c]; cmap[c] = (uint8_t)prev; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K9b
+__global__ void __launch_bounds__(32) k_ans_tables(const uint32_t* __restrict__ cluster_hist,
+                                                   const ClusterState* __restrict__ st, uint16_t* __restrict__ norm,
+                                                   uint16_t* __restrict__ rmap, AnsSymInfo* __restrict__ info,
+                                                   uint32_t* __restrict__ hdr_bits, uint32_t* __restrict__ hdr_len) {
+  __shared__ uint16_t s_norm[kAcAlphabet];
+  __shared__ uint16_t s_scratch[1024];
+  const int k = blockIdx.x, lane = threadIdx.x;
+  if (k >= st->num_clusters) return;
+  if (lane == 0) {
+    normalize_counts(cluster_hist + (size_t)k * kAcAlphabet, kAcAlphabet, s_norm);
+    BitWriterDev w;
+    w.init(hdr_bits + (size_t)k * 64);
+    write_ans_histogram(s_norm, kAcAlphabet, w);
+    w.flush();
+    hdr_len[k] = w.bits();
+  }
+  __syncwarp();
+  for (int s = lane; s < kAcAlphabet; s += 32) norm[(size_t)k * kAcAlphabet + s] = s_norm[s];
+  build_reverse_map(s_norm, kAcAlphabet, s_scratch, rmap + (size_t)k * kAnsTabSize, info + (size_t)k * kAcAlphabet, lane);
+}
+
+// ------------------------------------------------------------------------------------------ K10
+// The group's stream is written backwards so that it ENDS at word `kTokensPerGroupMax` of the
+// group's arena; start_bit[g] receives the position of its first bit inside the arena.
+__global__ void __launch_bounds__(32) k_ans_groups(const uint32_t* __restrict__ tokens,
+                                                   const uint32_t* __restrict__ token_counts,
+                                                   const uint8_t* __restrict__ cmap_g, const AnsSymInfo* __restrict__ info,
+                                                   const uint16_t* __restrict__ rmap, uint32_t* __restrict__ out_arena,
+                                                   unsigned long long* __restrict__ start_bit) {
+  __shared__ uint8_t s_cmap[kNumAcContexts + 7];
+  const int g = blockIdx.x, lane = threadIdx.x;
+  for (int i = lane; i < kNumAcContexts; i += 32) s_cmap[i] = cmap_g[i];
+  __syncwarp();
+  const uint32_t* tk = tokens + (size_t)g * kTokensPerGroupMax;
+  uint32_t* out = out_arena + (size_t)g * kTokensPerGroupMax;
+  const int n = (int)token_counts[g];
+  BackWriterDev bw;
+  bw.init(out, kTokensPerGroupMax);
+  uint32_t state = kAnsInitState;
+  for (int hi = n; hi > 0; hi -= 32) {
+    const int i = hi - 1 - lane;  // lane 0 owns the LAST token of the chunk
+    uint32_t freq = 0, rcp = 0, rbase = 0, xb = 0;
+    if (i >= 0) {
+      const uint32_t tkn = tk[i];
+      const uint32_t cl = s_cmap[tkn >> 16];
+      uint32_t tok, nb, bits;
+      hybrid_encode(tkn & 0xFFFF, tok, nb, bits);
+      const AnsSymInfo si = info[cl * kAcAlphabet + tok];
+      freq = si.freq; rcp = si.rcp; rbase = cl * kAnsTabSize + si.base;
+      xb = (nb << 16) | bits;  // nb <= 14, bits < 2^14
+    }
+    const int m = min(32, hi);
+    for (int j = 0; j < m; ++j) {
+      const uint32_t f = __shfl_sync(0xffffffffu, freq, j);
+      const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
+      const uint32_t rb = __shfl_sync(0xffffffffu, rbase, j);
+      const uint32_t x = __shfl_sync(0xffffffffu, xb, j);
+      bw.push((int)(x >> 16), x & 0xFFFF, lane == 0);
+      uint32_t o16;
+      if (ans_put(state, f, rc, rmap + rb, o16)) bw.push(16, o16, lane == 0);
+    }
+  }
+  bw.push(32, state, lane == 0);
+  const long long sb = bw.finish(lane == 0);
+  if (lane == 0) start_bit[g] = (unsigned long long)sb;
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+size_t cluster_state_bytes() { return sizeof(ClusterState); }
+
+void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* nzcount, const uint16_t* lastk,
+                     const int16_t* coeffs, const FrameDim& fd, uint32_t* tokens, uint32_t* token_counts, uint32_t* hist,
+                     cudaStream_t s) {
+  ++g_kernel_launches;
+  k_tokenize<<<fd.num_groups, 256, 0, s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
+}
+
+void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,
+                    cudaStream_t s) {
+  ++g_kernel_launches;
+  k_cluster<<<kClusterCtas, kClusterThreads, 0, s>>>(hist, lut, (ClusterState*)state, cmap, cluster_hist, kMaxClusters);
+}
+
+void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t* norm, uint16_t* rmap, void* info,
+                       uint32_t* hdr_bits, uint32_t* hdr_len, cudaStream_t s) {
+  ++g_kernel_launches;
+  k_ans_tables<<<kMaxClusters, 32, 0, s>>>(cluster_hist, (const ClusterState*)state, norm, rmap, (AnsSymInfo*)info,
+                                           hdr_bits, hdr_len);
+}
+
+void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
+                       const uint16_t* rmap, uint32_t* out_arena, unsigned long long* start_bit, int num_groups,
+                       cudaStream_t s) {
+  ++g_kernel_launches;
+  k_ans_groups<<<num_groups, 32, 0, s>>>(tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, out_arena, start_bit);
+}
+
+int cluster_num_clusters_offset() { return (int)offsetof(ClusterState, num_clusters); }
+
+}  // namespace jxlb

@@ -22,5 +22,47 @@ void launch_homogeneity(const float* x, const float* y, const float* b, const Fr
 void launch_dct8_quant(const float* x, const float* y, const float* b, const FrameDim& fd, const QuantDev* qd,
                        const float* weights, const float* dequant_y, const uint8_t* izz, const int8_t* cmap,
                        float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                       uint8_t* nzeros, uint8_t* lastpos, cudaStream_t s);
+                       uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
+
+// ---- entropy stage -------------------------------------------------------------------------
+// one 2048x2048 DC group: rectangle in blocks, its 64x64-tile rectangle, first element / first block slot
+struct DcGroupInfo { int x0, y0, w, h, tw, th; uint32_t elem_base; uint32_t block_base; };
+// one TOC section: where its bits live (kind 0 LfGlobal, 1 modular stream words, 2 HfGlobal, 3 AC group arena)
+struct Section { int kind; int index; unsigned long long src_bit, nbits, dst_bit; };
+
+// K8-K10 (k_entropy.cu)
+size_t cluster_state_bytes();
+int cluster_num_clusters_offset();
+void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* nzcount, const uint16_t* lastk,
+                     const int16_t* coeffs, const FrameDim& fd, uint32_t* tokens, uint32_t* token_counts, uint32_t* hist,
+                     cudaStream_t s);
+void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,
+                    cudaStream_t s);
+void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t* norm, uint16_t* rmap, void* info,
+                       uint32_t* hdr_bits, uint32_t* hdr_len, cudaStream_t s);
+void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
+                       const uint16_t* rmap, uint32_t* out_arena, unsigned long long* start_bit, int num_groups,
+                       cudaStream_t s);
+// K11 (k_modular.cu)
+void launch_tree_blob(int num_dc_groups, uint32_t* tree_words, uint32_t* tree_bits, cudaStream_t s);
+void launch_mod_ranks(const uint8_t* acs, const int32_t* raw_qf, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
+                      int32_t* strat_c, int32_t* qf_c, uint32_t* first_count, cudaStream_t s);
+void launch_mod_tokens(const int16_t* dc_quant, const int8_t* cmap, const int32_t* strat_c, const int32_t* qf_c,
+                       const uint32_t* first_count, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
+                       uint32_t total_elems, uint32_t* tokens, uint32_t* mod_hist, cudaStream_t s);
+void launch_mod_codes(const uint32_t* mod_hist, const QuantDev* qd, const uint32_t* tree_words, const uint32_t* tree_bits,
+                      uint8_t* code_len, uint16_t* code_bits, uint32_t* lf_words, uint32_t* lf_bits, cudaStream_t s);
+void launch_mod_write(const uint32_t* tokens, const uint8_t* code_len, const uint16_t* code_bits, const DcGroupInfo* dgs,
+                      int num_dg, const uint32_t* first_count, uint32_t total_elems, uint32_t* tile_sums, uint32_t* total_bits,
+                      uint32_t* words, uint32_t* dg_start_bit, cudaStream_t s);
+// K12 (k_assemble.cu)
+void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32_t* hdr_bits, const uint32_t* hdr_len,
+                      int num_groups, uint32_t* cm_back, uint32_t* hf_words, uint32_t* hf_bits, cudaStream_t s);
+void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
+                     const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
+                     Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
+                     unsigned long long* out_info, cudaStream_t s);
+void launch_assemble(const Section* sections, int num_sections, const uint32_t* lf_words, const uint32_t* mod_words,
+                     const uint32_t* hf_words, const uint32_t* group_arena, uint32_t* out_words,
+                     const unsigned long long* out_info, cudaStream_t s);
 }  // namespace jxlb

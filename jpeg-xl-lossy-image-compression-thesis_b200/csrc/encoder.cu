@@ -224,8 +224,9 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
                     stream_);
   CUDA_OK(cudaEventRecord(ev_[8], stream_));
   // K10: one rANS stream per AC group
-  launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_group_arena_.p, d_group_start_.p,
-                    fd.num_groups, stream_);
+  const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
+  launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_num_clusters, d_group_arena_.p,
+                    d_group_start_.p, fd.num_groups, stream_);
   CUDA_OK(cudaEventRecord(ev_[9], stream_));
   // K11: modular DC + AC metadata streams, LfGlobal
   uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;
@@ -246,7 +247,6 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
                    d_tile_sums_.p, mod_total_bits, d_mod_words_.p, d_dg_start_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[10], stream_));
   // K12: HfGlobal, headers + TOC, concatenation
-  const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
   launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
                    hf_bits, stream_);
   launch_finalize(fd, x_qm_scale_, b_qm_scale_, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,

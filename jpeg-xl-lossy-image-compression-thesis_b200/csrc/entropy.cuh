@@ -15,7 +15,7 @@ constexpr uint32_t kAnsInitState = 0x13u << 16;
 constexpr int kLogAlphaSize = 8;
 constexpr int kAcAlphabet = 64;
 constexpr int kModAlphabet = 128;
-constexpr int kMaxClusters = 64;
+constexpr int kMaxClusters = 24;  // 24 reverse maps x 8 KB = 192 KB: one SM's shared memory holds them all
 constexpr int kNumOrders = 13;
 constexpr int kNonZeroBuckets = 37;
 constexpr int kZeroDensityContextCount = 458;
@@ -230,6 +230,143 @@ __device__ __forceinline__ bool ans_put(uint32_t& state, uint32_t freq, uint32_t
   if (r >= freq) { ++q; r -= freq; }
   state = (q << kAnsLogTabSize) + rmap_sym[r];
   return emit;
+}
+
+// ---- prefix (Huffman) codes, warp-cooperative ------------------------------------------------
+// Deterministic Huffman, identical to the oracle's BuildPrefixCode: repeatedly merge the two
+// smallest nodes by (weight, node index) — leaves are indexed by symbol (< 128), internal nodes by
+// 128 + creation order, which is the oracle's (weight, id) order — with a doubling count floor until
+// no code is longer than 15 bits; canonical codes, bit-reversed for the LSB-first stream.
+struct HuffScratch { unsigned long long weight[2 * kModAlphabet]; short parent[2 * kModAlphabet]; uint8_t alive[2 * kModAlphabet]; };
+
+__device__ __forceinline__ bool huff_less(unsigned long long wa, int ia, unsigned long long wb, int ib) {
+  return wa < wb || (wa == wb && ia < ib);
+}
+
+__device__ inline void build_prefix_code_warp(const uint32_t* counts_in, HuffScratch& hs, uint8_t* length, uint16_t* code_bits,
+                                              int* alphabet_out, int lane) {
+  const unsigned full = 0xffffffffu;
+  uint32_t cnt[4];
+  int used = 0, last = -1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = lane + 32 * j;
+    cnt[j] = counts_in[s];
+    length[s] = 0; code_bits[s] = 0;
+    if (cnt[j]) { ++used; last = s; }
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) { used += __shfl_xor_sync(full, used, d); last = max(last, __shfl_xor_sync(full, last, d)); }
+  if (used == 0 || (used == 1 && last == 0)) { if (lane == 0) *alphabet_out = 1; __syncwarp(); return; }
+  if (used == 1) { if (lane == 0) cnt[0] = 1; used = 2; }   // a complex prefix code needs two coded symbols
+  if (lane == 0) *alphabet_out = last + 1;
+  for (uint32_t floor_count = 1;; floor_count *= 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = lane + 32 * j;
+      hs.alive[s] = cnt[j] ? 1 : 0;
+      hs.weight[s] = cnt[j] > floor_count ? cnt[j] : floor_count;
+      hs.parent[s] = -1;
+      hs.alive[128 + s] = 0; hs.parent[128 + s] = -1;
+    }
+    __syncwarp();
+    int created = 0;
+    for (int live = used; live > 1; --live) {
+      // per-lane two smallest among nodes lane, lane + 32, ...
+      unsigned long long w1 = ~0ull, w2 = ~0ull; int i1 = 0x7fff, i2 = 0x7fff;
+      const int nn = 128 + created;
+      for (int i = lane; i < nn; i += 32) {
+        if (!hs.alive[i]) continue;
+        const unsigned long long w = hs.weight[i];
+        if (huff_less(w, i, w1, i1)) { w2 = w1; i2 = i1; w1 = w; i1 = i; }
+        else if (huff_less(w, i, w2, i2)) { w2 = w; i2 = i; }
+      }
+      unsigned long long wa = w1; int ia = i1;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long ow = __shfl_xor_sync(full, wa, d); const int oi = __shfl_xor_sync(full, ia, d);
+        if (huff_less(ow, oi, wa, ia)) { wa = ow; ia = oi; }
+      }
+      unsigned long long wb = (i1 == ia) ? w2 : w1; int ib = (i1 == ia) ? i2 : i1;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long ow = __shfl_xor_sync(full, wb, d); const int oi = __shfl_xor_sync(full, ib, d);
+        if (huff_less(ow, oi, wb, ib)) { wb = ow; ib = oi; }
+      }
+      if (lane == 0) {
+        hs.weight[nn] = wa + wb; hs.parent[nn] = -1; hs.alive[nn] = 1;
+        hs.parent[ia] = (short)nn; hs.parent[ib] = (short)nn; hs.alive[ia] = 0; hs.alive[ib] = 0;
+      }
+      ++created;
+      __syncwarp();
+    }
+    int maxlen = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int s = lane + 32 * j;
+      int dpt = 0;
+      if (cnt[j]) for (int v = s; hs.parent[v] >= 0; v = hs.parent[v]) ++dpt;
+      length[s] = (uint8_t)dpt;
+      maxlen = max(maxlen, dpt);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) maxlen = max(maxlen, __shfl_xor_sync(full, maxlen, d));
+    __syncwarp();
+    if (maxlen <= 15) break;
+  }
+  if (lane == 0) {
+    uint32_t next_code[17];
+    uint32_t count[17];
+    for (int l = 0; l < 17; ++l) count[l] = 0;
+    for (int s = 0; s <= last; ++s) count[length[s]]++;
+    uint32_t code = 0;
+    for (int l = 1; l <= 15; ++l) { next_code[l] = code; code = (code + count[l]) << 1; }
+    for (int s = 0; s <= last; ++s) {
+      const int l = length[s];
+      if (l) code_bits[s] = (uint16_t)(__brev(next_code[l]++) >> (32 - l));
+    }
+  }
+  __syncwarp();
+}
+
+// complex prefix-code description (see the oracle's WritePrefixCodeHeader): 2 + 36 fixed bits, then
+// one bit-reversed 4-bit length per symbol.  hdr: >= 18 zeroed words.  Returns the bit count.
+__device__ inline uint32_t write_prefix_header_warp(const uint8_t* length, int alphabet, uint32_t* hdr, int lane) {
+  if (alphabet <= 1) return 0;
+  if (lane == 0) {
+    // hskip = 0 (2 bits), then code-length-code lengths in order {1,2,3,4,0,5,17,6,16,7..15}: "01" for 4, "00" for 0
+    unsigned long long fixed = 0;
+    const int order[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+    for (int i = 0; i < 18; ++i) if (order[i] < 16) fixed |= 1ull << (2 + 2 * i);
+    atomicOr(&hdr[0], (uint32_t)fixed);
+    atomicOr(&hdr[1], (uint32_t)(fixed >> 32));
+  }
+  for (int s = lane; s < alphabet; s += 32) {
+    const uint32_t nib = __brev((uint32_t)length[s]) >> 28;
+    const int pos = 38 + 4 * s;
+    const unsigned long long v = (unsigned long long)nib << (pos & 31);
+    atomicOr(&hdr[pos >> 5], (uint32_t)v);
+    if ((pos & 31) > 28) atomicOr(&hdr[(pos >> 5) + 1], (uint32_t)(v >> 32));
+  }
+  __syncwarp();
+  return 38 + 4 * (uint32_t)alphabet;
+}
+
+// CTA-cooperative bit copy with OR semantics (dst words must start out zero where not yet written)
+__device__ inline void cta_bitcopy(uint32_t* dst, unsigned long long dst_bit, const uint32_t* src, unsigned long long src_bit,
+                                   unsigned long long nbits, int t, int nthreads) {
+  if (nbits == 0) return;
+  const unsigned long long d0 = dst_bit, d1 = dst_bit + nbits;
+  for (unsigned long long wi = (d0 >> 5) + t; wi < ((d1 + 31) >> 5); wi += nthreads) {
+    const unsigned long long lo = max(wi << 5, d0), hi = min((wi + 1) << 5, d1);
+    const int n = (int)(hi - lo);
+    const unsigned long long sp = src_bit + (lo - d0);
+    const int sh = (int)(sp & 31);
+    uint32_t v = src[sp >> 5] >> sh;
+    if (sh + n > 32) v |= src[(sp >> 5) + 1] << (32 - sh);
+    if (n < 32) v &= (1u << n) - 1;
+    atomicOr(&dst[wi], v << (int)(lo & 31));
+  }
 }
 
 // backward bit writer: chunks are prepended, so the stream read forward lists them in the

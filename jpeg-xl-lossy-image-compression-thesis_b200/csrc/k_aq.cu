@@ -226,18 +226,40 @@ __device__ uint32_t radix_select(const float* __restrict__ v, size_t n, size_t k
     const int nb = 1 << bits[pass];
     for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const float f = kDeviation ? fabsf(v[i] - center) : v[i];
-      const uint32_t u = __float_as_uint(f);
-      const bool match = done_bits == 0 ? true : ((u >> (32 - done_bits)) == (prefix >> (32 - done_bits)));
-      if (match) atomicAdd(&hist[(u >> shifts[pass]) & (nb - 1)], 1u);
+    // the field is narrow-ranged, so most values share a digit: aggregate equal digits inside the
+    // warp (match.any) and let one lane per distinct digit do the shared-memory atomic
+    for (size_t i0 = 0; i0 < n; i0 += blockDim.x) {
+      const size_t i = i0 + threadIdx.x;
+      bool match = false;
+      uint32_t digit = 0;
+      if (i < n) {
+        const float f = kDeviation ? fabsf(v[i] - center) : v[i];
+        const uint32_t u = __float_as_uint(f);
+        match = done_bits == 0 ? true : ((u >> (32 - done_bits)) == (prefix >> (32 - done_bits)));
+        digit = (u >> shifts[pass]) & (nb - 1);
+      }
+      const unsigned part = __ballot_sync(0xffffffffu, match);
+      if (match) {
+        const unsigned peers = __match_any_sync(part, digit);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t acc = 0; int b = 0;
-      for (; b < nb; ++b) { if (acc + hist[b] > kk) break; acc += hist[b]; }
-      *sh_k = kk - acc;
-      *sh_prefix = prefix | ((uint32_t)b << shifts[pass]);
+    if (threadIdx.x < 32) {
+      // warp 0: each lane sums a contiguous run of nb/32 bins, warp scan picks the run, the owning lane the bin
+      const int per = nb / 32, lane = threadIdx.x;
+      uint32_t run = 0;
+      for (int b = lane * per; b < (lane + 1) * per; ++b) run += hist[b];
+      uint32_t incl = run;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+      const uint32_t excl = incl - run;
+      if (excl <= kk && kk < incl) {
+        uint32_t acc = excl; int b = lane * per;
+        for (; b < (lane + 1) * per; ++b) { if (acc + hist[b] > kk) break; acc += hist[b]; }
+        *sh_k = kk - acc;
+        *sh_prefix = prefix | ((uint32_t)b << shifts[pass]);
+      }
     }
     __syncthreads();
     kk = *sh_k; prefix = *sh_prefix;

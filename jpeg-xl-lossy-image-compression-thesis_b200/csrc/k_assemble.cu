@@ -7,22 +7,34 @@
 
 namespace jxlb {
 
-// ---- HfGlobal: context map (ANS coded, no MTF) + the per-cluster uint configs and histograms
+// ---- HfGlobal: context map (prefix coded, no MTF: every entry's bit length is known independently,
+// so the 7425 entries are placed by a CTA-wide scan and written in parallel) + the per-cluster
+// uint configs and histogram headers, concatenated with a cooperative bit copy.
 __global__ void __launch_bounds__(256) k_hf_global(const uint8_t* __restrict__ cmap, const int* __restrict__ num_clusters_p,
                                                    const uint32_t* __restrict__ hdr_bits, const uint32_t* __restrict__ hdr_len,
-                                                   int num_groups, uint32_t* __restrict__ cm_back, uint32_t* __restrict__ hf_words,
+                                                   int num_groups, uint32_t* __restrict__ cm_words, uint32_t* __restrict__ hf_words,
                                                    uint32_t* __restrict__ hf_bits) {
-  __shared__ uint32_t s_hist[kAcAlphabet];
-  __shared__ uint16_t s_norm[kAcAlphabet];
-  __shared__ uint16_t s_scratch[1024];
-  __shared__ uint16_t s_rmap[kAnsTabSize];
-  __shared__ AnsSymInfo s_info[kAcAlphabet];
-  __shared__ long long s_start;
-  constexpr int kBackWords = 8192;
+  __shared__ uint32_t s_hist[kModAlphabet];
+  __shared__ HuffScratch s_hs;
+  __shared__ uint8_t s_len[kModAlphabet];
+  __shared__ uint16_t s_code[kModAlphabet];
+  __shared__ int s_alpha;
+  __shared__ uint32_t s_pc_hdr[20];
+  __shared__ uint32_t s_pc_hdr_bits;
+  __shared__ uint32_t s_head[32], s_tail[16];
+  __shared__ uint32_t s_head_bits, s_tail_bits, s_cm_bits;
+  __shared__ uint32_t s_warp[8];
+  __shared__ unsigned long long s_piece_dst[kMaxClusters + 1];
+  constexpr int kCmWords = 8192;
+  constexpr int kPer = (kNumAcContexts + 255) / 256;  // 30 entries per thread
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int K = *num_clusters_p;
-  if (t < kAcAlphabet) s_hist[t] = 0;
+  for (int i = t; i < kModAlphabet; i += 256) s_hist[i] = 0;
+  if (t < 20) s_pc_hdr[t] = 0;
+  for (int i = t; i < kCmWords; i += 256) cm_words[i] = 0;
+  for (int i = t; i < 8192 + kMaxClusters * 64 + 256; i += 256) hf_words[i] = 0;
   __syncthreads();
+  uint32_t cm_bits = 0;
   if (K > 1) {
     for (int i = t; i < kNumAcContexts; i += 256) {
       uint32_t tk, nb, bits;
@@ -30,41 +42,39 @@ __global__ void __launch_bounds__(256) k_hf_global(const uint8_t* __restrict__ c
       atomicAdd(&s_hist[tk], 1u);
     }
     __syncthreads();
-    if (t == 0) normalize_counts(s_hist, kAcAlphabet, s_norm);
-    __syncthreads();
     if (warp == 0) {
-      build_reverse_map(s_norm, kAcAlphabet, s_scratch, s_rmap, s_info, lane);
-      BackWriterDev bw;
-      bw.init(cm_back, kBackWords);
-      uint32_t state = kAnsInitState;
-      for (int hi = kNumAcContexts; hi > 0; hi -= 32) {
-        const int i = hi - 1 - lane;
-        uint32_t freq = 0, rcp = 0, rbase = 0, xb = 0;
-        if (i >= 0) {
-          uint32_t tk, nb, bits;
-          hybrid_encode(cmap[i], tk, nb, bits);
-          freq = s_info[tk].freq; rcp = s_info[tk].rcp; rbase = s_info[tk].base; xb = (nb << 16) | bits;
-        }
-        const int m = min(32, hi);
-        for (int j = 0; j < m; ++j) {
-          const uint32_t f = __shfl_sync(0xffffffffu, freq, j);
-          const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
-          const uint32_t rb = __shfl_sync(0xffffffffu, rbase, j);
-          const uint32_t x = __shfl_sync(0xffffffffu, xb, j);
-          bw.push((int)(x >> 16), x & 0xFFFF, lane == 0);
-          uint32_t o16;
-          if (ans_put(state, f, rc, s_rmap + rb, o16)) bw.push(16, o16, lane == 0);
-        }
-      }
-      bw.push(32, state, lane == 0);
-      const long long sb = bw.finish(lane == 0);
-      if (lane == 0) s_start = sb;
+      build_prefix_code_warp(s_hist, s_hs, s_len, s_code, &s_alpha, lane);
+      const uint32_t hb = write_prefix_header_warp(s_len, s_alpha, s_pc_hdr, lane);
+      if (lane == 0) s_pc_hdr_bits = hb;
     }
+    __syncthreads();
+    // per-thread chunk of consecutive entries: total length, CTA scan, then write
+    const int i0 = min(t * kPer, kNumAcContexts), i1 = min(i0 + kPer, kNumAcContexts);
+    uint32_t sum = 0;
+    for (int i = i0; i < i1; ++i) { uint32_t tk, nb, bits; hybrid_encode(cmap[i], tk, nb, bits); sum += s_len[tk] + nb; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t pos = incl - sum;
+    for (int w = 0; w < warp; ++w) pos += s_warp[w];
+    if (t == 255) s_cm_bits = pos + sum;
+    for (int i = i0; i < i1; ++i) {
+      uint32_t tk, nb, bits;
+      hybrid_encode(cmap[i], tk, nb, bits);
+      const uint32_t cl = s_len[tk];
+      const unsigned long long v = ((unsigned long long)s_code[tk] | ((unsigned long long)bits << cl)) << (pos & 31);
+      atomicOr(&cm_words[pos >> 5], (uint32_t)v);
+      if ((pos & 31) + cl + nb > 32) atomicOr(&cm_words[(pos >> 5) + 1], (uint32_t)(v >> 32));
+      pos += cl + nb;
+    }
+    __syncthreads();
+    cm_bits = s_cm_bits;
   }
-  __syncthreads();
   if (t == 0) {
     BitWriterDev w;
-    w.init(hf_words);
+    w.init(s_head);
     w.write(1, 1);                                                  // default dequant matrices
     const int lg = num_groups <= 1 ? 0 : 32 - __clz(num_groups - 1);
     w.write(lg, 0);                                                 // num_histograms - 1
@@ -73,23 +83,30 @@ __global__ void __launch_bounds__(256) k_hf_global(const uint8_t* __restrict__ c
     if (K == 1) { w.write(1, 1); w.write(2, 0); }
     else {
       w.write(1, 0); w.write(1, 0);                                 // not simple, no MTF
-      w.write(1, 0); w.write(1, 0); w.write(2, kLogAlphaSize - 5);  // nested code: no lz77, ANS, alphabet 2^8
+      w.write(1, 0); w.write(1, 1);                                 // nested code: no lz77, prefix code
       w.write(4, 4); w.write(3, 2); w.write(2, 0);
-      write_ans_histogram(s_norm, kAcAlphabet, w);
-      const long long sb = s_start;
-      for (long long p = sb; p < (long long)kBackWords * 32;) {
-        const int n = (int)min((long long)(32 - (p & 31)), (long long)kBackWords * 32 - p);
-        w.write(n, (cm_back[p >> 5] >> (p & 31)) & (n == 32 ? 0xFFFFFFFFu : ((1u << n) - 1)));
-        p += n;
-      }
+      w.var_len_uint16((uint32_t)(s_alpha - 1));
+      w.append(s_pc_hdr, s_pc_hdr_bits);
     }
-    w.write(1, 0);                                                  // ANS
-    w.write(2, kLogAlphaSize - 5);
-    for (int k = 0; k < K; ++k) { w.write(4, 4); w.write(3, 2); w.write(2, 0); }
-    for (int k = 0; k < K; ++k) w.append(hdr_bits + (size_t)k * 64, hdr_len[k]);
     w.flush();
-    *hf_bits = w.bits();
+    s_head_bits = w.bits();
+    BitWriterDev w2;
+    w2.init(s_tail);
+    w2.write(1, 0);                                                 // ANS
+    w2.write(2, kLogAlphaSize - 5);
+    for (int k = 0; k < K; ++k) { w2.write(4, 4); w2.write(3, 2); w2.write(2, 0); }
+    w2.flush();
+    s_tail_bits = w2.bits();
+    unsigned long long pos = (unsigned long long)s_head_bits + cm_bits + s_tail_bits;
+    for (int k = 0; k < K; ++k) { s_piece_dst[k] = pos; pos += hdr_len[k]; }
+    s_piece_dst[K] = pos;
+    *hf_bits = (uint32_t)pos;
   }
+  __syncthreads();
+  cta_bitcopy(hf_words, 0, s_head, 0, s_head_bits, t, 256);
+  cta_bitcopy(hf_words, s_head_bits, cm_words, 0, cm_bits, t, 256);
+  cta_bitcopy(hf_words, (unsigned long long)s_head_bits + cm_bits, s_tail, 0, s_tail_bits, t, 256);
+  for (int k = warp; k < K; k += 8) cta_bitcopy(hf_words, s_piece_dst[k], hdr_bits + (size_t)k * 64, 0, hdr_len[k], lane, 32);
 }
 
 // ---- headers + TOC + section placement

@@ -37,22 +37,21 @@ __constant__ uint8_t c_nnz_ctx[64] = {0,   0,   31,  62,  62,  93,  93,  93,  93
                                       206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
 
 // ------------------------------------------------------------------------------------------ K8
-__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
-                                                  const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
-                                                  const int16_t* __restrict__ coeffs, FrameDim fd,
-                                                  uint32_t* __restrict__ tokens, uint32_t* __restrict__ token_counts,
-                                                  uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(1024) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
+                                                   const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
+                                                   const int16_t* __restrict__ coeffs, FrameDim fd,
+                                                   uint32_t* __restrict__ tokens, uint32_t* __restrict__ token_counts,
+                                                   uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_off[3072 + 1];
-  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_warp[32];
   const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int gx0 = (g % fd.gxs) * 32, gy0 = (g / fd.gxs) * 32;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
-  // ---- token count per (block, slot): 12 consecutive entries per thread = 4 blocks
-  uint32_t cnt[12];
+  // ---- token count per (block, slot): thread t = block t of the group
+  uint32_t cnt[3];
   uint32_t sum = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int blk = t * 4 + i, lx = blk & 31, ly = blk >> 5;
+  {
+    const int lx = t & 31, ly = t >> 5;
     const int bx = gx0 + lx, by = gy0 + ly;
     const bool inside = bx < fd.bxs && by < fd.bys;
     uint8_t a = 0;
@@ -69,11 +68,10 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
         const int nz = nzcount[bi];
         v = 1 + (nz ? (uint32_t)(lastk[bi] - n + 1) : 0u);
       }
-      cnt[i * 3 + slot] = v;
+      cnt[slot] = v;
       sum += v;
     }
   }
-  // CTA-wide exclusive scan of the per-thread sums
   uint32_t incl = sum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
@@ -82,12 +80,12 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
   uint32_t base = incl - sum;
   for (int w = 0; w < warp; ++w) base += s_warp[w];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { s_off[t * 12 + i] = base; base += cnt[i]; }
-  if (t == 255) { s_off[3072] = base; token_counts[g] = base; }
+  for (int i = 0; i < 3; ++i) { s_off[t * 3 + i] = base; base += cnt[i]; }
+  if (t == 1023) { s_off[3072] = base; token_counts[g] = base; }
   __syncthreads();
   // ---- emit: one warp per (block, slot)
   uint32_t* out = tokens + (size_t)g * kTokensPerGroupMax;
-  for (int e = warp; e < 3072; e += 8) {
+  for (int e = warp; e < 3072; e += 32) {
     const uint32_t off = s_off[e];
     const uint32_t count = s_off[e + 1] - off;
     if (count == 0) continue;
@@ -149,13 +147,11 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
 constexpr int kClusterCtas = 8;
 constexpr int kClusterThreads = 512;
 constexpr int kClusterWarps = kClusterCtas * kClusterThreads / 32;  // 128
+constexpr int kCtxSlots = (kNumAcContexts + kClusterWarps * 32 - 1) / (kClusterWarps * 32);  // 2
 
 struct ClusterState {   // global scratch
-  long long dist[kNumAcContexts];
   int assign[kNumAcContexts];
   uint32_t total[kNumAcContexts];
-  int list[kNumAcContexts];
-  int list_len;
   int num_clusters;
 };
 
@@ -168,6 +164,9 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // candidate ordering for the argmax: larger key first, lower context index on ties
 __device__ __forceinline__ bool better(long long ka, int ca, long long kb, int cb) { return ka > kb || (ka == kb && ca < cb); }
 
+// Context ownership is static: warp w of the 128 owns contexts w, w + 128, w + 256, ...; lane i keeps
+// (total, dist, assign) of the warp's i-th and (i + 32)-th context in registers for the whole
+// kernel, so a round only loads the histogram rows themselves.
 __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterThreads)
     k_cluster(const uint32_t* __restrict__ hist, const int* __restrict__ lut_g, ClusterState* __restrict__ st,
               uint8_t* __restrict__ cmap, uint32_t* __restrict__ cluster_hist, int max_clusters) {
@@ -183,28 +182,42 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
   const int rank = (int)cluster.block_rank();
   const int gwarp = rank * (kClusterThreads / 32) + warp;
   for (int i = t; i < 1025; i += kClusterThreads) s_lut[i] = lut_g[i];
-  if (rank == 0 && t == 0) st->list_len = 0;
   __syncthreads();
-  cluster.sync();
-  // ---- phase A: totals, list of non-empty contexts, first seed = largest total
-  long long best_key = -1; int best_ctx = 0x7fffffff;
-  for (int c = gwarp; c < kNumAcContexts; c += kClusterWarps) {
-    const uint32_t* h = hist + (size_t)c * kAcAlphabet;
-    uint32_t v = h[lane] + h[lane + 32];
+  // ---- phase A: totals of the owned contexts
+  uint32_t my_total[kCtxSlots];
+  long long my_dist[kCtxSlots];
+  int my_assign[kCtxSlots];
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane == 0) {
-      st->total[c] = v;
-      st->dist[c] = v ? 0x7fffffffffffffffll : -1;
-      st->assign[c] = 0;
-      if (v) { st->list[atomicAdd(&st->list_len, 1)] = c; }
+  for (int sl = 0; sl < kCtxSlots; ++sl) { my_total[sl] = 0; my_dist[sl] = -1; my_assign[sl] = 0; }
+#pragma unroll
+  for (int sl = 0; sl < kCtxSlots; ++sl) {
+    for (int i = 0; i < 32; ++i) {
+      const int c = gwarp + (sl * 32 + i) * kClusterWarps;
+      if (c >= kNumAcContexts) break;
+      const uint32_t* h = hist + (size_t)c * kAcAlphabet;
+      uint32_t v = h[lane] + h[lane + 32];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == i) { my_total[sl] = v; my_dist[sl] = v ? 0x7fffffffffffffffll : -1; }
     }
-    if (v && better((long long)v, c, best_key, best_ctx)) { best_key = (long long)v; best_ctx = c; }
+  }
+  long long best_key = -1; int best_ctx = 0x7fffffff;
+#pragma unroll
+  for (int sl = 0; sl < kCtxSlots; ++sl) {
+    const int c = gwarp + (sl * 32 + lane) * kClusterWarps;
+    if (my_total[sl] && better((long long)my_total[sl], c, best_key, best_ctx)) { best_key = (long long)my_total[sl]; best_ctx = c; }
+    if (c < kNumAcContexts) st->total[c] = my_total[sl];
   }
   int K = 0;
   int parity = 0;
   for (;;) {
-    // ---- cluster-wide argmax of (best_key, best_ctx) over all warps
+    // ---- cluster-wide argmax of (best_key, best_ctx): lanes -> warp -> CTA -> cluster (DSMEM)
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const long long ok = __shfl_xor_sync(0xffffffffu, best_key, d);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_ctx, d);
+      if (better(ok, oc, best_key, best_ctx)) { best_key = ok; best_ctx = oc; }
+    }
     if (lane == 0) { s_wkey[warp] = best_key; s_wctx[warp] = best_ctx; }
     __syncthreads();
     if (t == 0) {
@@ -231,48 +244,61 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
       s_xb[t] = xlogx(b, s_lut);
     }
     __syncthreads();
-    const uint32_t tb = st->total[seed];
+    uint32_t tb = 0;
+    for (int s = 0; s < kAcAlphabet; ++s) tb += s_hb[s];      // 64 broadcast LDS: cheaper than another barrier
     const long long xtb = xlogx(tb, s_lut);
     best_key = -1; best_ctx = 0x7fffffff;
-    const int n_list = st->list_len;
-    for (int i = gwarp; i < n_list; i += kClusterWarps) {
-      const int c = st->list[i];
-      const uint32_t* h = hist + (size_t)c * kAcAlphabet;
-      long long acc = 0;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int s = lane + 32 * half;
-        const uint32_t a = h[s], b = s_hb[s];
-        if (a && b) acc += xlogx(a + b, s_lut) - xlogx(a, s_lut) - s_xb[s];
+    for (int sl = 0; sl < kCtxSlots; ++sl) {
+      unsigned mask = __ballot_sync(0xffffffffu, my_total[sl] != 0);
+      while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int c = gwarp + (sl * 32 + i) * kClusterWarps;
+        const uint32_t* h = hist + (size_t)c * kAcAlphabet;
+        long long acc = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int s = lane + 32 * half;
+          const uint32_t a = h[s], b = s_hb[s];
+          if (a && b) acc += xlogx(a + b, s_lut) - xlogx(a, s_lut) - s_xb[s];
+        }
+        acc = warp_sum_ll(acc);
+        if (lane == i) {
+          const uint32_t ta = my_total[sl];
+          long long d = xlogx(ta + tb, s_lut) - xlogx(ta, s_lut) - xtb - acc;
+          if (c == seed) d = 0;
+          if (d < my_dist[sl]) { my_dist[sl] = d; my_assign[sl] = k; }
+        }
       }
-      acc = warp_sum_ll(acc);
-      const uint32_t ta = st->total[c];
-      long long d = xlogx(ta + tb, s_lut) - xlogx(ta, s_lut) - xtb - acc;
-      if (c == seed) d = 0;
-      long long cur = st->dist[c];
-      if (d < cur) {
-        cur = d;
-        if (lane == 0) { st->dist[c] = d; st->assign[c] = k; }
-      }
-      if (better(cur, c, best_key, best_ctx)) { best_key = cur; best_ctx = c; }
+      const int c = gwarp + (sl * 32 + lane) * kClusterWarps;
+      if (my_total[sl] && better(my_dist[sl], c, best_key, best_ctx)) { best_key = my_dist[sl]; best_ctx = c; }
     }
     __syncthreads();  // s_hb / s_xb are rewritten next round
     if (K >= max_clusters) break;
   }
   if (K == 0) K = 1;
-  cluster.sync();
-  // ---- cluster histograms (sum of members) and the context map
-  {
-    const int n_list = st->list_len;
-    for (int i = gwarp; i < n_list; i += kClusterWarps) {
-      const int c = st->list[i];
-      const int k = st->assign[c];
+#pragma unroll
+  for (int sl = 0; sl < kCtxSlots; ++sl) {
+    const int c = gwarp + (sl * 32 + lane) * kClusterWarps;
+    if (c < kNumAcContexts) st->assign[c] = my_assign[sl];
+  }
+  // ---- cluster histograms (sum of members)
+#pragma unroll
+  for (int sl = 0; sl < kCtxSlots; ++sl) {
+    unsigned mask = __ballot_sync(0xffffffffu, my_total[sl] != 0);
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int c = gwarp + (sl * 32 + i) * kClusterWarps;
+      const int k = __shfl_sync(0xffffffffu, my_assign[sl], i);
       const uint32_t* h = hist + (size_t)c * kAcAlphabet;
       for (int s = lane; s < kAcAlphabet; s += 32) { const uint32_t v = h[s]; if (v) atomicAdd(&cluster_hist[k * kAcAlphabet + s], v); }
     }
   }
+  cluster.sync();
   if (rank == 0) {
-    // empty contexts inherit the cluster of the previous non-empty context (0 before the first)
+    // context map: empty contexts inherit the cluster of the previous non-empty context (0 before the first)
     __shared__ int s_carry[kClusterThreads];
     constexpr int kChunk = (kNumAcContexts + kClusterThreads - 1) / kClusterThreads;
     const int c0 = t * kChunk, c1 = min(c0 + kChunk, kNumAcContexts);
@@ -314,49 +340,126 @@ __global__ void __launch_bounds__(32) k_ans_tables(const uint32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ K10
-// The group's stream is written backwards so that it ENDS at word `kTokensPerGroupMax` of the
-// group's arena; start_bit[g] receives the position of its first bit inside the arena.
-__global__ void __launch_bounds__(32) k_ans_groups(const uint32_t* __restrict__ tokens,
-                                                   const uint32_t* __restrict__ token_counts,
-                                                   const uint8_t* __restrict__ cmap_g, const AnsSymInfo* __restrict__ info,
-                                                   const uint16_t* __restrict__ rmap, uint32_t* __restrict__ out_arena,
-                                                   unsigned long long* __restrict__ start_bit) {
-  __shared__ uint8_t s_cmap[kNumAcContexts + 7];
-  const int g = blockIdx.x, lane = threadIdx.x;
-  for (int i = lane; i < kNumAcContexts; i += 32) s_cmap[i] = cmap_g[i];
-  __syncwarp();
+// One warp per AC group, kAnsWarps groups per CTA.  The CTA first stages EVERY table the chain
+// touches in shared memory (reverse maps of all clusters, symbol info, context map: <= 212 KB),
+// so the state-dependent lookup of each rANS step is an LDS (29 cycles) instead of an L1/L2 miss.
+// Per 32 tokens: lanes fetch + classify one token each (the next chunk's tokens are prefetched
+// while the current chain runs); the serial chain runs over shuffles and only computes the
+// state, each lane capturing its own token's renormalisation word; then the 32 variable-length
+// pieces are placed by a warp prefix sum and ORed into a 34-word shared staging window that is
+// stored with coalesced 32-bit writes.  The stream is produced back to front and ENDS at word
+// kTokensPerGroupMax of the group's arena; start_bit[g] = position of its first bit.
+constexpr int kAnsWarps = 4;
+constexpr int kStageWords = 34;
+
+__global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* __restrict__ tokens,
+                                                               const uint32_t* __restrict__ token_counts,
+                                                               const uint8_t* __restrict__ cmap_g,
+                                                               const AnsSymInfo* __restrict__ info_g,
+                                                               const uint16_t* __restrict__ rmap_g,
+                                                               const int* __restrict__ num_clusters_p, int num_groups,
+                                                               uint32_t* __restrict__ out_arena,
+                                                               unsigned long long* __restrict__ start_bit) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int K = *num_clusters_p;
+  uint16_t* s_rmap = reinterpret_cast<uint16_t*>(smem);                                  // [K][4096]
+  AnsSymInfo* s_info = reinterpret_cast<AnsSymInfo*>(smem + (size_t)K * kAnsTabSize * 2);  // [K][64]
+  uint8_t* s_cmap = reinterpret_cast<uint8_t*>(s_info + (size_t)K * kAcAlphabet);          // [7425 -> 7440]
+  uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_cmap + 7440);                          // [warps][34]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
+    uint4* dst = reinterpret_cast<uint4*>(s_rmap);
+    for (int i = t; i < K * kAnsTabSize / 8; i += kAnsWarps * 32) dst[i] = src[i];
+    const uint2* si = reinterpret_cast<const uint2*>(info_g);
+    uint2* di = reinterpret_cast<uint2*>(s_info);
+    for (int i = t; i < K * kAcAlphabet; i += kAnsWarps * 32) di[i] = si[i];
+    for (int i = t; i < kNumAcContexts; i += kAnsWarps * 32) s_cmap[i] = cmap_g[i];
+  }
+  __syncthreads();
+  const int g = blockIdx.x * kAnsWarps + warp;
+  if (g >= num_groups) return;
   const uint32_t* tk = tokens + (size_t)g * kTokensPerGroupMax;
   uint32_t* out = out_arena + (size_t)g * kTokensPerGroupMax;
+  uint32_t* stage = s_stage + warp * kStageWords;
   const int n = (int)token_counts[g];
-  BackWriterDev bw;
-  bw.init(out, kTokensPerGroupMax);
   uint32_t state = kAnsInitState;
+  long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
+  uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
+  uint32_t next_tok = (n - 1 - lane) >= 0 ? tk[n - 1 - lane] : 0;
   for (int hi = n; hi > 0; hi -= 32) {
     const int i = hi - 1 - lane;  // lane 0 owns the LAST token of the chunk
-    uint32_t freq = 0, rcp = 0, rbase = 0, xb = 0;
+    uint32_t freq = 4096, rcp = 0xFFFFFFFFu, rbase = 0, nb = 0, bits = 0;
     if (i >= 0) {
-      const uint32_t tkn = tk[i];
+      const uint32_t tkn = next_tok;
       const uint32_t cl = s_cmap[tkn >> 16];
-      uint32_t tok, nb, bits;
+      uint32_t tok;
       hybrid_encode(tkn & 0xFFFF, tok, nb, bits);
-      const AnsSymInfo si = info[cl * kAcAlphabet + tok];
+      const AnsSymInfo si = s_info[cl * kAcAlphabet + tok];
       freq = si.freq; rcp = si.rcp; rbase = cl * kAnsTabSize + si.base;
-      xb = (nb << 16) | bits;  // nb <= 14, bits < 2^14
     }
+    { const int in = hi - 32 - 1 - lane; next_tok = in >= 0 ? tk[in] : 0; }   // prefetch the next chunk
     const int m = min(32, hi);
+    uint32_t my_o16 = 0; int my_emit = 0;
     for (int j = 0; j < m; ++j) {
       const uint32_t f = __shfl_sync(0xffffffffu, freq, j);
       const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
       const uint32_t rb = __shfl_sync(0xffffffffu, rbase, j);
-      const uint32_t x = __shfl_sync(0xffffffffu, xb, j);
-      bw.push((int)(x >> 16), x & 0xFFFF, lane == 0);
-      uint32_t o16;
-      if (ans_put(state, f, rc, rmap + rb, o16)) bw.push(16, o16, lane == 0);
+      const bool emit = (state >> (32 - kAnsLogTabSize)) >= f;
+      if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
+      if (emit) state >>= 16;
+      uint32_t q = __umulhi(state, rc);
+      uint32_t r = state - q * f;
+      if (r >= f) { ++q; r -= f; }
+      state = (q << kAnsLogTabSize) + s_rmap[rb + r];
+    }
+    // ---- place the chunk's pieces: lane j's piece = [renorm word (16)][extra bits (nb)], earlier lanes later in the stream
+    const int len = (lane < m) ? (int)nb + (my_emit ? 16 : 0) : 0;
+    const uint32_t val = my_emit ? (my_o16 | (bits << 16)) : bits;
+    int incl = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const long long lo_bit = end_bit - total;                 // first stream bit of this chunk
+    const long long base_word = lo_bit >> 5;                  // lowest word touched
+    const long long top_word = end_bit >> 5;                  // word holding `carry` (if end_bit is unaligned)
+    const int nwords = (int)(((end_bit + 31) >> 5) - base_word);  // words covering [lo_bit, end_bit): <= 31
+    stage[lane] = 0;
+    if (lane < 2) stage[32 + lane] = 0;
+    __syncwarp();
+    if (lane == 0 && (end_bit & 31)) stage[top_word - base_word] = carry;
+    __syncwarp();
+    if (len) {
+      const long long p = end_bit - incl;                     // stream position of my piece
+      const int off = (int)(p - (base_word << 5));
+      const unsigned long long v = (unsigned long long)val << (off & 31);
+      atomicOr(&stage[off >> 5], (uint32_t)v);
+      if ((off & 31) + len > 32) atomicOr(&stage[(off >> 5) + 1], (uint32_t)(v >> 32));
+    }
+    __syncwarp();
+    // words strictly above the (possibly partial) lowest word are final
+    const int first_final = (lo_bit & 31) ? 1 : 0;
+    for (int w = first_final + lane; w < nwords; w += 32) {
+      if (base_word + w < (long long)kTokensPerGroupMax) out[base_word + w] = stage[w];
+    }
+    carry = stage[0];
+    __syncwarp();
+    end_bit = lo_bit;
+  }
+  // final state (32 bits) in front, then flush the partial word
+  {
+    const long long lo_bit = end_bit - 32;
+    const long long base_word = lo_bit >> 5;
+    if (lane == 0) {
+      const int sh = (int)(lo_bit & 31);
+      if (sh == 0) out[base_word] = state;
+      else {
+        out[base_word + 1] = (carry & ~((1u << sh) - 1)) | (state >> (32 - sh));   // carry holds bits >= sh of that word
+        out[base_word] = state << sh;
+      }
+      start_bit[g] = (unsigned long long)lo_bit;
     }
   }
-  bw.push(32, state, lane == 0);
-  const long long sb = bw.finish(lane == 0);
-  if (lane == 0) start_bit[g] = (unsigned long long)sb;
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -366,7 +469,7 @@ void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* 
                      const int16_t* coeffs, const FrameDim& fd, uint32_t* tokens, uint32_t* token_counts, uint32_t* hist,
                      cudaStream_t s) {
   ++g_kernel_launches;
-  k_tokenize<<<fd.num_groups, 256, 0, s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
+  k_tokenize<<<fd.num_groups, 1024, 0, s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
 }
 
 void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,
@@ -383,10 +486,18 @@ void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t
 }
 
 void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
-                       const uint16_t* rmap, uint32_t* out_arena, unsigned long long* start_bit, int num_groups,
-                       cudaStream_t s) {
+                       const uint16_t* rmap, const int* num_clusters, uint32_t* out_arena, unsigned long long* start_bit,
+                       int num_groups, cudaStream_t s) {
+  static bool configured = false;
+  const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
+                      kAnsWarps * kStageWords * 4;
+  if (!configured) {
+    cudaFuncSetAttribute(k_ans_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
   ++g_kernel_launches;
-  k_ans_groups<<<num_groups, 32, 0, s>>>(tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, out_arena, start_bit);
+  k_ans_groups<<<(num_groups + kAnsWarps - 1) / kAnsWarps, kAnsWarps * 32, smem, s>>>(
+      tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, num_clusters, num_groups, out_arena, start_bit);
 }
 
 int cluster_num_clusters_offset() { return (int)offsetof(ClusterState, num_clusters); }

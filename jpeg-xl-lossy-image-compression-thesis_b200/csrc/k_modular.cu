@@ -35,34 +35,36 @@ __global__ void __launch_bounds__(1024) k_mod_ranks(const uint8_t* __restrict__ 
                                                     int32_t* __restrict__ strat_c, int32_t* __restrict__ qf_c,
                                                     uint32_t* __restrict__ first_count) {
   __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
   const DcGroupInfo d = dgs[blockIdx.x];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int total = d.w * d.h;
-  const int per = (total + 1023) / 1024;
-  const int i0 = min(t * per, total), i1 = min(i0 + per, total);
-  uint32_t cnt = 0;
-  for (int i = i0; i < i1; ++i) {
-    const int x = i % d.w, y = i / d.w;
-    cnt += (acs[(size_t)(d.y0 + y) * fd.bxs + d.x0 + x] >> 7) & 1;
-  }
-  uint32_t incl = cnt;
-#pragma unroll
-  for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= dd) incl += o; }
-  if (lane == 31) s_warp[warp] = incl;
+  if (t == 0) s_carry = 0;
   __syncthreads();
-  uint32_t base = incl - cnt;
-  for (int w = 0; w < warp; ++w) base += s_warp[w];
-  if (t == 1023) first_count[blockIdx.x] = base + cnt;
-  for (int i = i0; i < i1; ++i) {
-    const int x = i % d.w, y = i / d.w;
-    const size_t bi = (size_t)(d.y0 + y) * fd.bxs + d.x0 + x;
-    const uint8_t a = acs[bi];
-    if (a & 0x80) {
-      strat_c[d.block_base + base] = a & 0x7f;
-      qf_c[d.block_base + base] = raw_qf[bi] - 1;
-      ++base;
+  for (int i0 = 0; i0 < total; i0 += 1024) {
+    const int i = i0 + t;
+    uint8_t a = 0; size_t bi = 0;
+    if (i < total) {
+      const int y = i / d.w, x = i - y * d.w;
+      bi = (size_t)(d.y0 + y) * fd.bxs + d.x0 + x;
+      a = acs[bi];
     }
+    const bool first = (a & 0x80) != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, first);
+    if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+    __syncthreads();
+    uint32_t base = s_carry;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    if (first) {
+      const uint32_t r = base + (uint32_t)__popc(bal & ((1u << lane) - 1));
+      strat_c[d.block_base + r] = a & 0x7f;
+      qf_c[d.block_base + r] = raw_qf[bi] - 1;
+    }
+    __syncthreads();
+    if (t == 1023) s_carry = base + (uint32_t)__popc(bal);
+    __syncthreads();
   }
+  if (t == 0) first_count[blockIdx.x] = s_carry;
 }
 
 // ---- tokens (leaf << 24 | packed residual) + per-leaf histograms
@@ -129,58 +131,6 @@ __global__ void __launch_bounds__(256) k_mod_tokens(const int16_t* __restrict__ 
 }
 
 // ---- Huffman codes of the 8 leaves (one warp each) and the LfGlobal section
-struct HuffScratch { unsigned long long weight[2 * kModAlphabet]; short parent[2 * kModAlphabet]; short id[2 * kModAlphabet]; uint8_t alive[2 * kModAlphabet]; short leaf_node[kModAlphabet]; };
-
-// Deterministic Huffman (merge the two smallest (weight, id); leaves id = symbol, internal
-// id = 256 + creation order; doubling count floor until max length <= 15) — same rule as the oracle.
-__device__ void build_prefix_code(const uint32_t* counts_in, HuffScratch& hs, uint8_t* length, uint16_t* code_bits, int* alphabet_out) {
-  uint32_t counts[kModAlphabet];
-  int used = 0, last = -1;
-  for (int s = 0; s < kModAlphabet; ++s) { counts[s] = counts_in[s]; length[s] = 0; code_bits[s] = 0; if (counts[s]) { ++used; last = s; } }
-  if (used == 0 || (used == 1 && last == 0)) { *alphabet_out = 1; return; }
-  if (used == 1) { counts[0] = 1; used = 2; }
-  *alphabet_out = last + 1;
-  for (uint32_t floor_count = 1;; floor_count *= 2) {
-    int n = 0;
-    for (int s = 0; s <= last; ++s) {
-      hs.leaf_node[s] = -1;
-      if (!counts[s]) continue;
-      hs.weight[n] = counts[s] > floor_count ? counts[s] : floor_count; hs.parent[n] = -1; hs.id[n] = (short)s; hs.alive[n] = 1;
-      hs.leaf_node[s] = (short)n++;
-    }
-    int live = n, created = 0;
-    while (live > 1) {
-      int a = -1, b = -1;
-      for (int i = 0; i < n; ++i) {
-        if (!hs.alive[i]) continue;
-        if (a < 0 || hs.weight[i] < hs.weight[a] || (hs.weight[i] == hs.weight[a] && hs.id[i] < hs.id[a])) { b = a; a = i; }
-        else if (b < 0 || hs.weight[i] < hs.weight[b] || (hs.weight[i] == hs.weight[b] && hs.id[i] < hs.id[b])) b = i;
-      }
-      hs.weight[n] = hs.weight[a] + hs.weight[b]; hs.parent[n] = -1; hs.id[n] = (short)(256 + created++); hs.alive[n] = 1;
-      hs.parent[a] = (short)n; hs.parent[b] = (short)n; hs.alive[a] = 0; hs.alive[b] = 0;
-      ++n; --live;
-    }
-    int maxlen = 0;
-    for (int s = 0; s <= last; ++s) {
-      if (hs.leaf_node[s] < 0) { length[s] = 0; continue; }
-      int dpt = 0;
-      for (int v = hs.leaf_node[s]; hs.parent[v] >= 0; v = hs.parent[v]) ++dpt;
-      length[s] = (uint8_t)dpt;
-      maxlen = max(maxlen, dpt);
-    }
-    if (maxlen <= 15) break;
-  }
-  uint32_t code = 0;
-  for (int len = 1; len <= 15; ++len) {
-    for (int s = 0; s <= last; ++s) {
-      if (length[s] != len) continue;
-      code_bits[s] = (uint16_t)(__brev(code) >> (32 - len));
-      ++code;
-    }
-    code <<= 1;
-  }
-}
-
 // global MA tree + its single-histogram ANS code (constant given num_dc_groups; see the oracle's
 // WriteGlobalTree for the node table).  Serial, ~80 tokens; runs on one lane.
 __device__ void write_global_tree(int num_dc_groups, BitWriterDev& w, uint16_t* s_scratch, uint16_t* s_rmap, AnsSymInfo* s_info,
@@ -244,8 +194,14 @@ __global__ void __launch_bounds__(256) k_mod_codes(const uint32_t* __restrict__ 
   __shared__ uint8_t s_len[kNumModularCtx][kModAlphabet];
   __shared__ uint16_t s_bits[kNumModularCtx][kModAlphabet];
   __shared__ int s_alpha[kNumModularCtx];
+  __shared__ uint32_t s_hdr[kNumModularCtx][20];
+  __shared__ uint32_t s_hdr_bits[kNumModularCtx];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (lane == 0) build_prefix_code(mod_hist + warp * kModAlphabet, s_hs[warp], s_len[warp], s_bits[warp], &s_alpha[warp]);
+  if (lane < 20) s_hdr[warp][lane] = 0;
+  __syncwarp();
+  build_prefix_code_warp(mod_hist + warp * kModAlphabet, s_hs[warp], s_len[warp], s_bits[warp], &s_alpha[warp], lane);
+  const uint32_t hb = write_prefix_header_warp(s_len[warp], s_alpha[warp], s_hdr[warp], lane);
+  if (lane == 0) s_hdr_bits[warp] = hb;
   __syncthreads();
   for (int i = t; i < kNumModularCtx * kModAlphabet; i += 256) { code_len[i] = s_len[i / kModAlphabet][i % kModAlphabet]; code_bits[i] = s_bits[i / kModAlphabet][i % kModAlphabet]; }
   if (t == 0) {
@@ -271,13 +227,7 @@ __global__ void __launch_bounds__(256) k_mod_codes(const uint32_t* __restrict__ 
     w.write(1, 1);                 // prefix codes
     for (int l = 0; l < kNumModularCtx; ++l) { w.write(4, 4); w.write(3, 2); w.write(2, 0); }
     for (int l = 0; l < kNumModularCtx; ++l) w.var_len_uint16((uint32_t)(s_alpha[l] - 1));
-    for (int l = 0; l < kNumModularCtx; ++l) {
-      if (s_alpha[l] <= 1) continue;
-      w.write(2, 0);
-      const int order[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
-      for (int i = 0; i < 18; ++i) w.write(2, order[i] >= 16 ? 0u : 1u);
-      for (int s = 0; s < s_alpha[l]; ++s) w.write(4, __brev((uint32_t)s_len[l][s]) >> 28);
-    }
+    for (int l = 0; l < kNumModularCtx; ++l) w.append(s_hdr[l], s_hdr_bits[l]);
     w.flush();
     *lf_bits = w.bits();
   }

@@ -317,26 +317,27 @@ void WriteContextMap(const uint8_t* cmap, int n, int num_clusters, BitWriter* w)
   if (num_clusters == 1) { w->Write(1, 1); w->Write(2, 0); return; }  // simple, 0 bits per entry
   w->Write(1, 0);  // not simple
   w->Write(1, 0);  // no move-to-front
-  // nested single-context ANS code over the hybrid-uint tokens of the entries
+  // nested single-context code over the hybrid-uint tokens of the entries: a PREFIX code, so that
+  // the 7425 entries can be written in parallel (an rANS chain would serialise them)
   w->Write(1, 0);  // lz77 disabled
-  w->Write(1, 0);  // ANS, not prefix
-  w->Write(2, kLogAlphaSize - 5);
-  w->Write(4, 4); w->Write(3, 2); w->Write(2, 0);  // uint config (4, 2, 0)
-  std::vector<uint32_t> counts(kAcAlphabet, 0), tokens(n);
+  w->Write(1, 1);  // prefix code
+  w->Write(4, 4); w->Write(3, 2); w->Write(2, 0);  // uint config (4, 2, 0) at log_alpha_size 15
+  std::vector<uint32_t> counts(kModAlphabet, 0);
   for (int i = 0; i < n; ++i) {
     uint32_t tok, nb, bits;
     HybridEncode(cmap[i], &tok, &nb, &bits);
     counts[tok]++;
-    tokens[i] = cmap[i];  // ctx 0
   }
-  AnsCode code;
-  code.num_clusters = 1; code.alphabet = kAcAlphabet;
-  code.norm.assign(kAcAlphabet, 0);
-  NormalizeCounts(counts.data(), kAcAlphabet, code.norm.data());
-  WriteAnsHistogram(code.norm.data(), kAcAlphabet, w);
-  code.Build();
-  const uint8_t zero = 0;
-  AnsWriteTokens(tokens.data(), (size_t)n, &zero, code, w);
+  PrefixCode pc;
+  BuildPrefixCode(counts.data(), kModAlphabet, &pc);
+  w->WriteVarLenUint16((uint32_t)(pc.alphabet - 1));
+  WritePrefixCodeHeader(pc, w);
+  for (int i = 0; i < n; ++i) {
+    uint32_t tok, nb, bits;
+    HybridEncode(cmap[i], &tok, &nb, &bits);
+    w->Write(pc.length[tok], pc.bits[tok]);
+    w->Write((int)nb, bits);
+  }
 }
 
 // ------------------------------------------------------------------ coefficient tokens (U6)

@@ -16,7 +16,7 @@ constexpr uint32_t kAnsSignature = 0x13;  // initial state 0x130000
 constexpr int kLogAlphaSize = 8;          // alias tables of 256 buckets x 16 slots
 constexpr int kAcAlphabet = 64;           // hybrid-uint (4,2,0) tokens of values < 2^16
 constexpr int kModAlphabet = 128;         // hybrid-uint (4,2,0) tokens of values < 2^32
-constexpr int kMaxClusters = 64;
+constexpr int kMaxClusters = 24;         // all reverse maps of one frame fit one SM's shared memory (24 x 8 KB)
 
 // block contexts (libjxl ac_context.h)
 constexpr int kNumOrders = 13;

@@ -386,32 +386,63 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t state = kAnsInitState;
   long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
   uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
-  uint32_t next_tok = (n - 1 - lane) >= 0 ? tk[n - 1 - lane] : 0;
-  for (int hi = n; hi > 0; hi -= 32) {
+  const uint32_t rmap_saddr = (uint32_t)__cvta_generic_to_shared(s_rmap);
+  int m = n > 0 ? ((n - 1) & 31) + 1 : 0;                  // the first chunk (stream tail) is the partial one
+  uint32_t next_tok = (n - 1 - lane) >= 0 && lane < m ? tk[n - 1 - lane] : 0;
+  for (int hi = n; hi > 0; hi -= m, m = 32) {
     const int i = hi - 1 - lane;  // lane 0 owns the LAST token of the chunk
-    uint32_t freq = 4096, rcp = 0xFFFFFFFFu, rbase = 0, nb = 0, bits = 0;
-    if (i >= 0) {
+    // per-token chain operands: freq | (shared byte address of the symbol's reverse-map run) << 13, reciprocal
+    uint32_t packed = 4096u, rcp = 0x00100000u, nb = 0, bits = 0;
+    if (lane < m) {
       const uint32_t tkn = next_tok;
       const uint32_t cl = s_cmap[tkn >> 16];
       uint32_t tok;
       hybrid_encode(tkn & 0xFFFF, tok, nb, bits);
       const AnsSymInfo si = s_info[cl * kAcAlphabet + tok];
-      freq = si.freq; rcp = si.rcp; rbase = cl * kAnsTabSize + si.base;
+      packed = si.freq | ((rmap_saddr + 2u * (cl * kAnsTabSize + si.base)) << 13);
+      rcp = si.rcp;
     }
-    { const int in = hi - 32 - 1 - lane; next_tok = in >= 0 ? tk[in] : 0; }   // prefetch the next chunk
-    const int m = min(32, hi);
+    { const int in = hi - m - 1 - lane; next_tok = in >= 0 ? tk[in] : 0; }   // prefetch the next (full) chunk
     uint32_t my_o16 = 0; int my_emit = 0;
-    for (int j = 0; j < m; ++j) {
-      const uint32_t f = __shfl_sync(0xffffffffu, freq, j);
-      const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
-      const uint32_t rb = __shfl_sync(0xffffffffu, rbase, j);
-      const bool emit = (state >> (32 - kAnsLogTabSize)) >= f;
-      if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
-      if (emit) state >>= 16;
-      uint32_t q = __umulhi(state, rc);
-      uint32_t r = state - q * f;
-      if (r >= f) { ++q; r -= f; }
-      state = (q << kAnsLogTabSize) + s_rmap[rb + r];
+    if (m == 32) {
+      // full chunk: broadcast all operands first (64 independent shuffles, pipelined), then run the
+      // 32-step chain on registers only: ISETP -> SEL -> IMAD.HI -> IMAD -> SEL -> LDS -> IMAD
+      uint32_t pf[32], prc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { pf[j] = __shfl_sync(0xffffffffu, packed, j); prc[j] = __shfl_sync(0xffffffffu, rcp, j); }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t f = pf[j] & 0x1FFF, tab_a = pf[j] >> 13;
+        uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;   // all off the state chain
+        // opaque to the optimiser, so that it keeps r = q * negf + x2 and the two parallel address forms
+        // instead of re-deriving them from f on the serial chain
+        asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
+        const bool emit = state > thr;
+        if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
+        const uint32_t x2 = emit ? (state >> 16) : state;
+        const uint32_t q = __umulhi(x2, prc[j]);
+        const uint32_t r = q * negf + x2;
+        const bool fix = r >= f;
+        const uint32_t a_lo = tab_a + 2 * r, a_hi = tab_b + 2 * r;
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
+        state = ((fix ? q + 1 : q) << kAnsLogTabSize) + v;
+      }
+    } else {
+      for (int j = 0; j < m; ++j) {
+        const uint32_t pk = __shfl_sync(0xffffffffu, packed, j);
+        const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
+        const uint32_t f = pk & 0x1FFF, tab = pk >> 13;
+        const bool emit = (state >> (32 - kAnsLogTabSize)) >= f;
+        if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
+        if (emit) state >>= 16;
+        uint32_t q = __umulhi(state, rc);
+        uint32_t r = state - q * f;
+        if (r >= f) { ++q; r -= f; }
+        uint16_t v;
+        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tab + 2 * r));
+        state = (q << kAnsLogTabSize) + v;
+      }
     }
     // ---- place the chunk's pieces: lane j's piece = [renorm word (16)][extra bits (nb)], earlier lanes later in the stream
     const int len = (lane < m) ? (int)nb + (my_emit ? 16 : 0) : 0;

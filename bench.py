@@ -5,8 +5,9 @@ dominant kernel and the CPU baseline beside it.
   python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
   python bench.py --impl reference ...                   (CPU arm: the oracle on the host cores)
 
-A step = one encode of one synthetic image of the workload (BASELINE.json configs[1]:
-3840x2160 RGB8, distance 1.0, fixed DCT8 strategy) per rank.  `value` is measured with the
+A step = one batch of `--batch` synthetic images of the workload (BASELINE.json configs[1]:
+3840x2160 RGB8, distance 1.0, fixed DCT8 strategy) per rank, `--pipelines` of them in flight
+(the reference keeps 6 workers busy the same way, benchmark-jpegxl/src/config.rs:22).  `value` is measured with the
 image resident in HBM (jxlb200_encode_device, CUDA events on the encoder's stream);
 `e2e` goes through jxlb200_encode with HOST buffers (pinned staging + H2D + kernels + D2H
 of the codestream inside the timed region).  Ranks shard by image (no data-path collective):
@@ -26,6 +27,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per pipeline stream (before CUDA init)
 sys.path.insert(0, ROOT)
 PKG = "jpeg-xl-lossy-image-compression-thesis_b200"
 
@@ -39,6 +41,9 @@ WORKLOADS = {
 }
 # algorithmic bytes per pixel of each pipeline stage (DESIGN.md "Kernels")
 STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
+# DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), per workload kernel;
+# filled from profiles/ (None = not captured for this kernel)
+TRAFFIC_BYTES = {"coeff": 125.3e6}
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -167,11 +172,13 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=32, help="images per rank per step")
+    ap.add_argument("--pipelines", type=int, default=16, help="images in flight per rank (CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -193,12 +200,16 @@ def main():
     pkg = importlib.import_module(PKG)
     w, h, distance, effort, proposal, flags = WORKLOADS[args.workload]
     mp = w * h / 1e6
-    n_img = 4                                    # distinct inputs per rank, rotated
-    imgs = [pkg.synth_image(w, h, rank * 16 + i) for i in range(n_img)]
-    d_imgs = [torch.from_numpy(im).cuda() for im in imgs]
+    B = args.batch                               # images per rank per step, args.pipelines of them in flight
+    imgs = [pkg.synth_image(w, h, rank * 64 + i) for i in range(B)]
+    pinned = [torch.from_numpy(im).pin_memory() for im in imgs]          # e2e inputs: page-locked host memory
+    h_imgs = [p.numpy() for p in pinned]
+    d_imgs = [p.cuda() for p in pinned]                                  # value inputs: resident in HBM
+    d_ptrs = [d.data_ptr() for d in d_imgs]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     enc = pkg.Encoder(local_rank)
+    enc.set_pipelines(args.pipelines)
 
     def barrier():
         torch.cuda.synchronize()
@@ -206,36 +217,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM, device time by CUDA events on the encoder's stream ----
+    # ---- value: inputs resident in HBM; CUDA-event time of each batch (all pipeline streams) ----
     for i in range(args.warmup):
-        enc.encode_device(d_imgs[i % n_img].data_ptr(), w, h, 3 * w, distance, effort, proposal, flags)
+        enc.encode_batch_device(d_ptrs, w, h, 3 * w, distance, effort, proposal, flags)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    dev_ms, stage_ms, launches = [], [], 0
+    dev_ms, launches = [], 0
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.fill_(i & 255)                     # L2 flush between timed iterations (untimed)
         torch.cuda.synchronize()
-        st = enc.encode_device(d_imgs[i % n_img].data_ptr(), w, h, 3 * w, distance, effort, proposal, flags)
-        dev_ms.append(st.total_ms)
-        stage_ms.append(list(st.stage_ms))
-        launches += st.kernel_launches
+        sts, ms = enc.encode_batch_device(d_ptrs, w, h, 3 * w, distance, effort, proposal, flags)
+        dev_ms.append(ms)
+        launches += sum(s.kernel_launches for s in sts)
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     total_ms = float(sum(dev_ms))
-    last_stats = st
+    last_stats = sts[-1]
 
-    # ---- e2e: host buffers through jxlb200_encode, wall clock around the calls ----
+    # ---- per-kernel times for the roofline: one image alone on the GPU (no overlap between streams) ----
+    stage_ms = []
+    for i in range(max(3, min(args.steps, 10))):
+        flush.fill_(i & 255)
+        torch.cuda.synchronize()
+        st1 = enc.encode_device(d_ptrs[i % B], w, h, 3 * w, distance, effort, proposal, flags)
+        stage_ms.append(list(st1.stage_ms) + [st1.total_ms])
+
+    # ---- e2e: pinned host buffers through jxlb200_encode_batch, wall clock around the calls ----
     for i in range(args.warmup):
-        enc.encode(imgs[i % n_img], distance, effort, proposal, flags)
+        enc.encode_batch(h_imgs, distance, effort, proposal, flags)
     barrier()
     t0 = time.perf_counter()
     out_bytes = 0
     for i in range(args.steps):
-        data, st2 = enc.encode(imgs[i % n_img], distance, effort, proposal, flags)
-        out_bytes += len(data)
+        data, st2 = enc.encode_batch(h_imgs, distance, effort, proposal, flags)
+        out_bytes += sum(len(d) for d in data)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -249,28 +267,39 @@ def main():
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
-        value = world * mp / (ms_per_step / 1e3)
-        e2e_value = world * mp * args.steps / e2e_s
-        # roofline of the dominant kernel stage (largest mean CUDA-event time among the HBM-bound stages)
+        value = world * B * mp / (ms_per_step / 1e3)
+        e2e_value = world * B * mp * args.steps / e2e_s
         mean_stage = np.mean(np.array(stage_ms), axis=0)
         peak, peak_kind = measured_peak_gbs()
-        dom = max(STAGE_BYTES_PER_PX, key=lambda s: mean_stage[STAGE_INDEX[s]])
+        # the HBM-bound kernel the north star names: transform + quantise (k_dct8_quant, 18.3 B/px)
+        dom = "coeff"
         dom_ms = float(mean_stage[STAGE_INDEX[dom]])
         achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "algorithmic_bytes_per_px": STAGE_BYTES_PER_PX[dom], "kernel_ms": dom_ms,
-                "stage_ms": {k: float(mean_stage[v]) for k, v in STAGE_INDEX.items()}}
+        per_stage = {}
+        for sname, bpp_alg in STAGE_BYTES_PER_PX.items():
+            t_ms = float(mean_stage[STAGE_INDEX[sname]])
+            per_stage[sname] = {"ms": t_ms, "GB/s": bpp_alg * w * h / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0,
+                                "frac": (bpp_alg * w * h / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else 0.0}
+        roof = {"bound": "hbm", "kernel": "k_dct8_quant (transform + quantise)", "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get(dom),
+                "algorithmic_bytes_per_launch": STAGE_BYTES_PER_PX[dom] * w * h, "kernel_ms": dom_ms,
+                "hbm_stages": per_stage,
+                "single_image_stage_ms": {k: float(mean_stage[v]) for k, v in STAGE_INDEX.items()},
+                "single_image_total_ms": float(mean_stage[-1]),
+                "note": "per-kernel times from single-image encodes (one stream); the largest stage, the per-group "
+                        "rANS chains (ans), is serial-latency bound, not bandwidth bound: see profiles/"}
         line = {
             "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "distance": distance, "effort": effort,
-                       "proposal": proposal, "flags": flags, "images_per_rank_per_step": 1,
-                       "l2": "flushed between timed iterations (256 MiB fill, untimed)",
+                       "proposal": proposal, "flags": flags, "images_per_rank_per_step": B,
+                       "pipelines_per_rank": args.pipelines,
+                       "l2": "flushed between timed iterations (256 MiB fill, untimed); inputs per step "
+                             f"{B * 3 * w * h >> 20} MiB",
                        "parallelism": f"image-sharded x{world}, no data-path collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": 3 * w * h,
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * 3 * w * h,
                     "d2h_bytes_per_step": out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": launches,
             "roofline": roof,

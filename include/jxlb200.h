@@ -132,9 +132,22 @@ int jxlb200_encode_device(jxlb200_ctx* ctx, const uint8_t* d_pixels, uint32_t wi
 int jxlb200_fetch(jxlb200_ctx* ctx, uint8_t** out, size_t* out_len);
 
 /* Batch form of the per-image loop of JXLCompressionBenchmark::run (benchmark.rs:637-660):
- * n images, n parameter sets, n outputs; images are pipelined over the context's streams. */
+ * n images, n parameter sets, n outputs; up to jxlb200_set_pipelines() images are in flight at once,
+ * each on its own CUDA stream.  Page-locked (pinned) input buffers are copied without staging. */
 int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jxlb200_params* params,
                          size_t n, uint8_t** outs, size_t* out_lens, jxlb200_stats* stats);
+
+/* Batch with the RGB8 images already resident in device memory; the codestreams stay on the device
+ * (their sizes are reported in stats[i].codestream_bytes).  Used for the HBM-resident throughput
+ * measurement. */
+int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels, const uint32_t* widths,
+                                const uint32_t* heights, const size_t* strides, const jxlb200_params* params, size_t n,
+                                jxlb200_stats* stats, float* device_ms /* may be NULL: CUDA-event time of the batch */);
+
+/* Number of images the batch entry points keep in flight (default 4, or $JXLB200_PIPELINES): each
+ * pipeline owns a CUDA stream and its device arenas, like each of the reference's num_workers = 6
+ * worker threads owns a container (benchmark-jpegxl/src/config.rs:22, benchmark.rs:173-198). */
+int jxlb200_set_pipelines(jxlb200_ctx* ctx, int n);
 
 /* Copies the intermediate `stage` of the LAST encode on this context to host memory.
  * Returns the stage size in bytes (copying only if cap is large enough), or < 0. */

@@ -6,6 +6,13 @@ Host-side mirror of the one encoder call the thesis harness makes,
 ``include/jxlb200.h`` (``libjxlb200.so``).  There is no CPU fallback: importing
 works anywhere, but creating an encoder without an sm_100 GPU raises.
 """
+import os as _os
+
+# The batch entry points keep up to 32 images in flight on separate CUDA streams; with the default of 8
+# hardware work queues several streams share a queue and serialise (measured: 4-way instead of 8-way
+# overlap).  Must be set before the CUDA context exists, hence at import time.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .encoder import (  # noqa: F401
     Encoder, EncodeError, Stats, PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY,
     PROPOSAL_COMBINED, FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, STAGES, frame_dims, library_path, load_library,

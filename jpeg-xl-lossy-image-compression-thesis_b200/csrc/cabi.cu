@@ -9,13 +9,33 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <vector>
+#include <algorithm>
 
 using namespace jxlb;
 
+// One context = a set of independent pipelines (each an Encoder with its own CUDA stream and device
+// arenas).  Single encodes use pipeline 0; the batch entry points keep several images in flight so
+// that the serial stages of one image (the per-group rANS chains) overlap the other images' work.
 struct jxlb200_ctx {
-  Encoder enc;
+  Encoder enc;                        // pipeline 0
+  std::vector<Encoder*> extra;        // pipelines 1..P-1, created on first batch use
+  int device = 0;
+  int num_pipelines = 4;
   std::string err;
+  Encoder* pipe(int i) { return i == 0 ? &enc : extra[i - 1]; }
 };
+
+static bool ensure_pipelines(jxlb200_ctx* ctx, int n) {
+  while ((int)ctx->extra.size() + 1 < n) {
+    Encoder* e = new Encoder();
+    std::string err;
+    if (!e->Init(ctx->device, &err)) { delete e; ctx->err = err; return false; }
+    ctx->extra.push_back(e);
+  }
+  return true;
+}
 
 static int fail(jxlb200_ctx* ctx, const std::string& msg, int code = -1) {
   if (ctx) ctx->err = msg;
@@ -27,12 +47,16 @@ extern "C" {
 int jxlb200_abi_version(void) { return JXLB200_ABI_VERSION; }
 
 jxlb200_ctx* jxlb200_create(int device) {
+  // one hardware work queue per pipeline stream; only effective when the CUDA context does not exist yet
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return nullptr;
   if (prop.major != 10) return nullptr;  // sm_100a only; there is no fallback path
   jxlb200_ctx* ctx = new jxlb200_ctx();
+  ctx->device = device;
+  if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 32) ctx->num_pipelines = v; }
   std::string e;
   if (!ctx->enc.Init(device, &e)) { delete ctx; return nullptr; }
   return ctx;
@@ -41,6 +65,7 @@ jxlb200_ctx* jxlb200_create(int device) {
 void jxlb200_destroy(jxlb200_ctx* ctx) {
   if (!ctx) return;
   ctx->enc.Destroy();
+  for (Encoder* e : ctx->extra) { e->Destroy(); delete e; }
   delete ctx;
 }
 
@@ -64,6 +89,7 @@ int jxlb200_encode_device(jxlb200_ctx* ctx, const uint8_t* d_pixels, uint32_t wi
   if (stride < (size_t)3 * width) return fail(ctx, "stride smaller than 3*width");
   std::string e;
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
+  ctx->enc.set_ans_groups_per_warp(1);
   if (!ctx->enc.EncodeDevice(d_pixels, (int)width, (int)height, stride, ep, stats, &e)) return fail(ctx, e);
   return 0;
 }
@@ -85,6 +111,7 @@ int jxlb200_encode(jxlb200_ctx* ctx, const jxlb200_image* image, const jxlb200_p
   if (image->stride < (size_t)3 * image->width) return fail(ctx, "stride smaller than 3*width");
   std::string e;
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
+  ctx->enc.set_ans_groups_per_warp(1);
   if (!ctx->enc.EncodeHost(image->pixels, (int)image->width, (int)image->height, image->stride, ep, stats, &e))
     return fail(ctx, e);
   if (!ctx->enc.Fetch(out, out_len, &e)) return fail(ctx, e);
@@ -94,10 +121,105 @@ int jxlb200_encode(jxlb200_ctx* ctx, const jxlb200_image* image, const jxlb200_p
 int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jxlb200_params* params, size_t n,
                          uint8_t** outs, size_t* out_lens, jxlb200_stats* stats) {
   if (!ctx) return -1;
+  if (!images || !params || !outs || !out_lens) return fail(ctx, "null argument");
   for (size_t i = 0; i < n; ++i) {
-    const int rc = jxlb200_encode(ctx, &images[i], &params[i], &outs[i], &out_lens[i], stats ? &stats[i] : nullptr);
-    if (rc) return rc;
+    outs[i] = nullptr; out_lens[i] = 0;
+    if (!images[i].pixels) return fail(ctx, "invalid image");
+    if (int rc = check_params(ctx, images[i].width, images[i].height, &params[i])) return rc;
+    if (images[i].stride < (size_t)3 * images[i].width) return fail(ctx, "stride smaller than 3*width");
   }
+  const int P = (int)std::min<size_t>((size_t)ctx->num_pipelines, n ? n : 1);
+  if (!ensure_pipelines(ctx, P)) return -1;
+  std::vector<long> owner(P, -1);   // image currently in flight on each pipeline
+  std::string e;
+  int rc = 0;
+  auto retire = [&](int p) {
+    const long i = owner[p];
+    if (i < 0) return;
+    owner[p] = -1;
+    if (!ctx->pipe(p)->Finish(stats ? &stats[i] : nullptr, &e) || !ctx->pipe(p)->Fetch(&outs[i], &out_lens[i], &e)) rc = fail(ctx, e);
+  };
+  for (size_t i = 0; i < n && rc == 0; ++i) {
+    const int p = (int)(i % P);
+    retire(p);
+    if (rc) break;
+    EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
+    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? 3 : 1);
+    if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
+      rc = fail(ctx, e);
+      break;
+    }
+    owner[p] = (long)i;
+  }
+  for (int k = 0; k < P; ++k) retire((int)((n + k) % P));   // oldest first
+  if (rc) for (size_t i = 0; i < n; ++i) { free(outs[i]); outs[i] = nullptr; out_lens[i] = 0; }
+  return rc;
+}
+
+int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels, const uint32_t* widths,
+                                const uint32_t* heights, const size_t* strides, const jxlb200_params* params, size_t n,
+                                jxlb200_stats* stats, float* device_ms) {
+  if (!ctx) return -1;
+  if (!d_pixels || !widths || !heights || !strides || !params) return fail(ctx, "null argument");
+  for (size_t i = 0; i < n; ++i) {
+    if (!d_pixels[i]) return fail(ctx, "invalid image");
+    if (int rc = check_params(ctx, widths[i], heights[i], &params[i])) return rc;
+    if (strides[i] < (size_t)3 * widths[i]) return fail(ctx, "stride smaller than 3*width");
+  }
+  const int P = (int)std::min<size_t>((size_t)ctx->num_pipelines, n ? n : 1);
+  if (!ensure_pipelines(ctx, P)) return -1;
+  std::vector<long> owner(P, -1);
+  std::string e;
+  int rc = 0;
+  double enqueue_us = 0.0;
+  // device time of the whole batch: every pipeline starts after `t0` and `t1` waits for all of them
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (device_ms) {
+    cudaSetDevice(ctx->device);
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, ctx->pipe(0)->stream());
+    for (int p = 1; p < P; ++p) cudaStreamWaitEvent(ctx->pipe(p)->stream(), t0, 0);
+  }
+  auto retire = [&](int p) {
+    const long i = owner[p];
+    if (i < 0) return;
+    owner[p] = -1;
+    if (!ctx->pipe(p)->Finish(stats ? &stats[i] : nullptr, &e)) rc = fail(ctx, e);
+  };
+  for (size_t i = 0; i < n && rc == 0; ++i) {
+    const int p = (int)(i % P);
+    retire(p);
+    if (rc) break;
+    EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
+    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? 3 : 1);
+    const auto tq0 = std::chrono::steady_clock::now();
+    if (!ctx->pipe(p)->EnqueueDevice(d_pixels[i], (int)widths[i], (int)heights[i], strides[i], ep, &e)) { rc = fail(ctx, e); break; }
+    enqueue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
+    owner[p] = (long)i;
+  }
+  if (device_ms) {
+    std::vector<cudaEvent_t> done(P, nullptr);
+    for (int p = 1; p < P; ++p) {
+      cudaEventCreateWithFlags(&done[p], cudaEventDisableTiming);
+      cudaEventRecord(done[p], ctx->pipe(p)->stream());
+      cudaStreamWaitEvent(ctx->pipe(0)->stream(), done[p], 0);
+    }
+    cudaEventRecord(t1, ctx->pipe(0)->stream());
+    cudaEventSynchronize(t1);
+    *device_ms = 0.0f;
+    cudaEventElapsedTime(device_ms, t0, t1);
+    for (int p = 1; p < P; ++p) cudaEventDestroy(done[p]);
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+  }
+  for (int k = 0; k < P; ++k) retire((int)((n + k) % P));
+  if (getenv("JXLB200_DEBUG")) fprintf(stderr, "[jxlb200] batch of %zu on %d pipelines: host enqueue %.1f us per image\n", n, P, enqueue_us / (double)(n ? n : 1));
+  return rc;
+}
+
+int jxlb200_set_pipelines(jxlb200_ctx* ctx, int n) {
+  if (!ctx) return -1;
+  if (n < 1 || n > 32) return fail(ctx, "pipelines out of range [1, 32]");
+  ctx->num_pipelines = n;
   return 0;
 }
 

@@ -63,10 +63,10 @@ bool Encoder::Init(int device, std::string* err) {
         d_rmap_.Reserve((size_t)kMaxClusters * kAnsTabSize) && d_mod_hist_.Reserve(kNumModularCtx * kModAlphabet) &&
         d_lf_words_.Reserve(4096) && d_small_.Reserve(16) && d_tree_words_.Reserve(256) &&
         d_code_len_.Reserve(kNumModularCtx * kModAlphabet) && d_code_bits_.Reserve(kNumModularCtx * kModAlphabet) &&
-        d_cm_back_.Reserve(8192) && d_hf_words_.Reserve(8192 + kMaxClusters * 64 + 256) && d_out_info_.Reserve(2))) {
+        d_cm_back_.Reserve(8192) && d_hf_words_.Reserve(8192 + kMaxClusters * 64 + 256) && d_out_info_.Reserve(8))) {
     *err = "alloc"; return false;
   }
-  CUDA_OK(cudaMallocHost(&h_out_info_, 2 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost(&h_out_info_, 8 * sizeof(unsigned long long)));
   if (!d_cvx_.Reserve(27) || !d_cvy_.Reserve(27) || !d_q_.Reserve(1)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_cvx_.p, kCoveredX, 27, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d_cvy_.p, kCoveredY, 27, cudaMemcpyHostToDevice));
@@ -122,6 +122,7 @@ bool Encoder::Reserve(const FrameDim& fd, std::string* err) {
     h_dgs_.push_back(d);
   }
   total_elems_ = elem;
+  const bool new_geometry = fd.xsize != dgs_w_ || fd.ysize != dgs_h_;
   const size_t nsec = (size_t)2 + fd.num_dc_groups + fd.num_groups;
   const size_t out_words = ((size_t)fd.xsize * fd.ysize * 4 + (1u << 20) + nsec * 8) / 4;
   ok = ok && d_tokens_.Reserve((size_t)fd.num_groups * kTokensPerGroupMax) && d_token_counts_.Reserve(fd.num_groups) &&
@@ -132,41 +133,67 @@ bool Encoder::Reserve(const FrameDim& fd, std::string* err) {
        d_dg_start_.Reserve(fd.num_dc_groups) && d_hdr_stage_.Reserve(nsec + 64) && d_sections_.Reserve(nsec) &&
        d_out_.Reserve(out_words);
   if (!ok) { *err = "device allocation failed"; return false; }
+  if (new_geometry) {
+    // (a pageable-memory copy inside the pipeline would make the host wait for the stream: do it here, once per geometry)
+    if (cudaMemcpy(d_dgs_.p, h_dgs_.data(), h_dgs_.size() * sizeof(DcGroupInfo), cudaMemcpyHostToDevice) != cudaSuccess) {
+      *err = "memcpy"; return false;
+    }
+    dgs_w_ = fd.xsize; dgs_h_ = fd.ysize;
+  }
   return true;
 }
 
-bool Encoder::EncodeHost(const uint8_t* pixels, int w, int h, size_t stride, const EncodeParams& p, jxlb200_stats* stats,
-                         std::string* err) {
+// true when `p` is page-locked host memory (cudaMallocHost / cudaHostRegister): it can be the source of a
+// truly asynchronous copy, so the staging memcpy is skipped
+static bool IsPinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+bool Encoder::EnqueueHost(const uint8_t* pixels, int w, int h, size_t stride, const EncodeParams& p, std::string* err) {
   CUDA_OK(cudaSetDevice(device_));
   const size_t row = (size_t)3 * w;
   const size_t bytes = row * h;
   if (!d_rgb_.Reserve(bytes + 16)) { *err = "device allocation failed"; return false; }
-  if (bytes > h_pinned_cap_) {
-    if (h_pinned_) cudaFreeHost(h_pinned_);
-    h_pinned_ = nullptr; h_pinned_cap_ = 0;
-    CUDA_OK(cudaMallocHost(&h_pinned_, bytes));
-    h_pinned_cap_ = bytes;
-  }
   CUDA_OK(cudaEventRecord(ev_[0], stream_));
-  // pack rows into the pinned staging buffer (drops any row padding), then one async copy
-  if (stride == row) memcpy(h_pinned_, pixels, bytes);
-  else for (int y = 0; y < h; ++y) memcpy(h_pinned_ + (size_t)y * row, pixels + (size_t)y * stride, row);
-  CUDA_OK(cudaMemcpyAsync(d_rgb_.p, h_pinned_, bytes, cudaMemcpyHostToDevice, stream_));
+  if (stride == row && IsPinned(pixels)) {
+    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, pixels, bytes, cudaMemcpyHostToDevice, stream_));
+  } else {
+    if (bytes > h_pinned_cap_) {
+      if (h_pinned_) cudaFreeHost(h_pinned_);
+      h_pinned_ = nullptr; h_pinned_cap_ = 0;
+      CUDA_OK(cudaMallocHost(&h_pinned_, bytes));
+      h_pinned_cap_ = bytes;
+    }
+    // pack rows into the pinned staging buffer (drops any row padding), then one async copy
+    if (stride == row) memcpy(h_pinned_, pixels, bytes);
+    else for (int y = 0; y < h; ++y) memcpy(h_pinned_ + (size_t)y * row, pixels + (size_t)y * stride, row);
+    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, h_pinned_, bytes, cudaMemcpyHostToDevice, stream_));
+  }
   fd_.Set(w, h);
-  return Run(d_rgb_.p, row, p, stats, true, err);
+  return Run(d_rgb_.p, row, p, err);
+}
+
+bool Encoder::EnqueueDevice(const uint8_t* d_pixels, int w, int h, size_t stride, const EncodeParams& p, std::string* err) {
+  CUDA_OK(cudaSetDevice(device_));
+  CUDA_OK(cudaEventRecord(ev_[0], stream_));
+  fd_.Set(w, h);
+  return Run(d_pixels, stride, p, err);
+}
+
+bool Encoder::EncodeHost(const uint8_t* pixels, int w, int h, size_t stride, const EncodeParams& p, jxlb200_stats* stats,
+                         std::string* err) {
+  return EnqueueHost(pixels, w, h, stride, p, err) && Finish(stats, err);
 }
 
 bool Encoder::EncodeDevice(const uint8_t* d_pixels, int w, int h, size_t stride, const EncodeParams& p,
                            jxlb200_stats* stats, std::string* err) {
-  CUDA_OK(cudaSetDevice(device_));
-  CUDA_OK(cudaEventRecord(ev_[0], stream_));
-  fd_.Set(w, h);
-  return Run(d_pixels, stride, p, stats, false, err);
+  return EnqueueDevice(d_pixels, w, h, stride, p, err) && Finish(stats, err);
 }
 
-bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jxlb200_stats* stats, bool h2d_timed,
-                  std::string* err) {
-  (void)h2d_timed;
+// Enqueues every kernel of one encode on the stream; nothing here waits for the device.
+bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err) {
   const FrameDim& fd = fd_;
   if (!Reserve(fd, err)) return false;
   params_ = p;
@@ -225,8 +252,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
   CUDA_OK(cudaEventRecord(ev_[8], stream_));
   // K10: one rANS stream per AC group
   const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
-  launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_num_clusters, d_group_arena_.p,
-                    d_group_start_.p, fd.num_groups, stream_);
+  launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_num_clusters, d_small_.p + 4,
+                    ans_groups_per_warp_, d_group_arena_.p, d_group_start_.p, fd.num_groups, stream_);
   CUDA_OK(cudaEventRecord(ev_[9], stream_));
   // K11: modular DC + AC metadata streams, LfGlobal
   uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;
@@ -235,7 +262,6 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
     launch_tree_blob(fd.num_dc_groups, d_tree_words_.p, tree_bits, stream_);
     tree_ndc_ = fd.num_dc_groups;
   }
-  CUDA_OK(cudaMemcpyAsync(d_dgs_.p, h_dgs_.data(), h_dgs_.size() * sizeof(DcGroupInfo), cudaMemcpyHostToDevice, stream_));
   CUDA_OK(cudaMemsetAsync(d_mod_hist_.p, 0, kNumModularCtx * kModAlphabet * 4, stream_));
   CUDA_OK(cudaMemsetAsync(d_mod_words_.p, 0, ((size_t)total_elems_ + 2) * 4, stream_));
   launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, stream_);
@@ -250,11 +276,23 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
   launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
                    hf_bits, stream_);
   launch_finalize(fd, x_qm_scale_, b_qm_scale_, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,
-                  d_sections_.p, d_hdr_stage_.p, d_out_.p, (unsigned long long)d_out_.cap * 32, d_out_info_.p, stream_);
+                  d_sections_.p, d_hdr_stage_.p, d_out_.p, (unsigned long long)d_out_.cap * 32, d_out_info_.p, d_q_.p,
+                  d_token_counts_.p, d_num_clusters, stream_);
   launch_assemble(d_sections_.p, 2 + fd.num_dc_groups + fd.num_groups, d_lf_words_.p, d_mod_words_.p, d_hf_words_.p,
                   d_group_arena_.p, d_out_.p, d_out_info_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[11], stream_));
-  CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  launches_ = g_kernel_launches;
+  in_flight_ = true;
+  return true;
+}
+
+// Waits for the encode enqueued last and collects its statistics.
+bool Encoder::Finish(jxlb200_stats* stats, std::string* err) {
+  if (!in_flight_) { *err = "no encode in flight"; return false; }
+  in_flight_ = false;
+  const FrameDim& fd = fd_;
+  CUDA_OK(cudaSetDevice(device_));
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
   if (h_out_info_[1]) { *err = "codestream larger than the output arena"; return false; }
@@ -264,10 +302,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
     memset(stats, 0, sizeof(*stats));
     stats->width = fd.xsize; stats->height = fd.ysize;
     stats->num_groups = fd.num_groups; stats->num_dc_groups = fd.num_dc_groups;
-    QuantDev q;
-    CUDA_OK(cudaMemcpy(&q, d_q_.p, sizeof(q), cudaMemcpyDeviceToHost));
-    stats->kernel_launches = g_kernel_launches;
-    stats->global_scale = q.global_scale; stats->quant_dc = q.quant_dc;
+    stats->kernel_launches = launches_;
+    stats->global_scale = (uint32_t)h_out_info_[2]; stats->quant_dc = (uint32_t)h_out_info_[3];
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_[0], ev_[1]); stats->stage_ms[JXLB200_T_H2D] = ms;
     cudaEventElapsedTime(&ms, ev_[1], ev_[2]); stats->stage_ms[JXLB200_T_XYB] = ms;
@@ -283,16 +319,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jx
     cudaEventElapsedTime(&ms, ev_[0], ev_[11]); stats->total_ms = ms;
     stats->codestream_bytes = codestream_bytes_;
     stats->bpp = 8.0 * (double)codestream_bytes_ / ((double)fd.xsize * fd.ysize);
-    {
-      std::vector<uint32_t> counts(fd.num_groups);
-      CUDA_OK(cudaMemcpy(counts.data(), d_token_counts_.p, counts.size() * 4, cudaMemcpyDeviceToHost));
-      uint64_t nt = 0;
-      for (uint32_t c : counts) nt += c;
-      stats->num_tokens = nt;
-      int k = 0;
-      CUDA_OK(cudaMemcpy(&k, d_cluster_state_.p + cluster_num_clusters_offset(), 4, cudaMemcpyDeviceToHost));
-      stats->num_clusters = (uint32_t)k;
-    }
+    stats->num_tokens = h_out_info_[4];
+    stats->num_clusters = (uint32_t)h_out_info_[5];
   }
   return true;
 }
@@ -302,7 +330,8 @@ bool Encoder::Fetch(uint8_t** out, size_t* out_len, std::string* err) {
   cudaSetDevice(device_);
   uint8_t* buf = (uint8_t*)malloc(codestream_bytes_ ? codestream_bytes_ : 1);
   if (!buf) { *err = "out of host memory"; return false; }
-  if (cudaMemcpy(buf, d_out_.p, codestream_bytes_, cudaMemcpyDeviceToHost) != cudaSuccess) { free(buf); *err = "memcpy"; return false; }
+  if (cudaMemcpyAsync(buf, d_out_.p, codestream_bytes_, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+      cudaStreamSynchronize(stream_) != cudaSuccess) { free(buf); *err = "memcpy"; return false; }
   *out = buf;
   *out_len = codestream_bytes_;
   return true;

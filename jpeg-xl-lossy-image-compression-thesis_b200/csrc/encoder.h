@@ -34,13 +34,22 @@ class Encoder {
                   std::string* err);
   bool EncodeDevice(const uint8_t* d_pixels, int w, int h, size_t stride, const EncodeParams& p, jxlb200_stats* stats,
                     std::string* err);
+  // asynchronous halves: Enqueue* only launches (H2D copy + kernels) on this encoder's stream, Finish waits
+  bool EnqueueHost(const uint8_t* pixels, int w, int h, size_t stride, const EncodeParams& p, std::string* err);
+  bool EnqueueDevice(const uint8_t* d_pixels, int w, int h, size_t stride, const EncodeParams& p, std::string* err);
+  bool Finish(jxlb200_stats* stats, std::string* err);
   bool Fetch(uint8_t** out, size_t* out_len, std::string* err);
   int64_t Dump(int stage, void* dst, size_t cap, std::string* err);
+  cudaStream_t stream() const { return stream_; }
+  // 1 = lowest latency (one group per warp); > 1 packs the rANS chains onto fewer SMs (batch throughput)
+  void set_ans_groups_per_warp(int n) { ans_groups_per_warp_ = n; }
 
  private:
   bool Reserve(const FrameDim& fd, std::string* err);
-  bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, jxlb200_stats* stats, bool h2d_timed,
-           std::string* err);
+  bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
+  bool in_flight_ = false;
+  int ans_groups_per_warp_ = 1;
+  unsigned launches_ = 0;
 
   int device_ = -1;
   cudaStream_t stream_ = nullptr;
@@ -79,6 +88,7 @@ class Encoder {
   std::vector<DcGroupInfo> h_dgs_;
   uint32_t total_elems_ = 0;
   int tree_ndc_ = -1;
+  int dgs_w_ = -1, dgs_h_ = -1;
   DevBuf<DcGroupInfo> d_dgs_;
   DevBuf<int32_t> d_strat_c_, d_qf_c_;
   DevBuf<uint32_t> d_first_count_, d_mod_tokens_, d_mod_hist_, d_lf_words_, d_small_, d_tile_sums_, d_mod_words_, d_dg_start_,

@@ -123,7 +123,19 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
                                                  const uint32_t* __restrict__ hf_bits, const unsigned long long* __restrict__ group_start_bit,
                                                  Section* __restrict__ sections, uint32_t* __restrict__ hdr_stage,
                                                  uint32_t* __restrict__ out_words, unsigned long long out_capacity_bits,
-                                                 unsigned long long* __restrict__ out_info) {
+                                                 unsigned long long* __restrict__ out_info, const QuantDev* __restrict__ qd,
+                                                 const uint32_t* __restrict__ token_counts,
+                                                 const int* __restrict__ num_clusters_p) {
+  {  // statistics block read back by the host together with the size (one pinned copy)
+    unsigned long long nt = 0;
+    for (int g = threadIdx.x; g < fd.num_groups; g += 32) nt += token_counts[g];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) nt += __shfl_xor_sync(0xffffffffu, nt, d);
+    if (threadIdx.x == 0) {
+      out_info[2] = (unsigned long long)qd->global_scale; out_info[3] = (unsigned long long)qd->quant_dc;
+      out_info[4] = nt; out_info[5] = (unsigned long long)*num_clusters_p;
+    }
+  }
   if (threadIdx.x != 0) return;
   const int ndc = fd.num_dc_groups, ng = fd.num_groups;
   const bool small = ng == 1;
@@ -232,10 +244,11 @@ void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32
 void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
                      const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
                      Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
-                     unsigned long long* out_info, cudaStream_t s) {
+                     unsigned long long* out_info, const QuantDev* qd, const uint32_t* token_counts, const int* num_clusters,
+                     cudaStream_t s) {
   ++g_kernel_launches;
   k_finalize<<<1, 32, 0, s>>>(fd, x_qm_scale, b_qm_scale, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
-                             sections, hdr_stage, out_words, out_capacity_bits, out_info);
+                             sections, hdr_stage, out_words, out_capacity_bits, out_info, qd, token_counts, num_clusters);
 }
 
 void launch_assemble(const Section* sections, int num_sections, const uint32_t* lf_words, const uint32_t* mod_words,

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(32) k_ans_tables(const uint32_t* __restrict__ 
 // pieces are placed by a warp prefix sum and ORed into a 34-word shared staging window that is
 // stored with coalesced 32-bit writes.  The stream is produced back to front and ENDS at word
 // kTokensPerGroupMax of the group's arena; start_bit[g] = position of its first bit.
-constexpr int kAnsWarps = 4;
+constexpr int kAnsWarps = 16;
 constexpr int kStageWords = 34;
 
 __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* __restrict__ tokens,
@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
                                                                const AnsSymInfo* __restrict__ info_g,
                                                                const uint16_t* __restrict__ rmap_g,
                                                                const int* __restrict__ num_clusters_p, int num_groups,
+                                                               uint32_t* __restrict__ work_counter,
                                                                uint32_t* __restrict__ out_arena,
                                                                unsigned long long* __restrict__ start_bit) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -377,7 +378,13 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
     for (int i = t; i < kNumAcContexts; i += kAnsWarps * 32) s_cmap[i] = cmap_g[i];
   }
   __syncthreads();
-  const int g = blockIdx.x * kAnsWarps + warp;
+  const uint32_t rmap_saddr = (uint32_t)__cvta_generic_to_shared(s_rmap);
+  // warps take groups from a shared counter (longest-processing-time order is not needed: a warp that
+  // drew a short group simply draws again), so a CTA stays resident only as long as it has work
+  for (;;) {
+  int g = 0;
+  if (lane == 0) g = (int)atomicAdd(work_counter, 1u);
+  g = __shfl_sync(0xffffffffu, g, 0);
   if (g >= num_groups) return;
   const uint32_t* tk = tokens + (size_t)g * kTokensPerGroupMax;
   uint32_t* out = out_arena + (size_t)g * kTokensPerGroupMax;
@@ -386,7 +393,6 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t state = kAnsInitState;
   long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
   uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
-  const uint32_t rmap_saddr = (uint32_t)__cvta_generic_to_shared(s_rmap);
   int m = n > 0 ? ((n - 1) & 31) + 1 : 0;                  // the first chunk (stream tail) is the partial one
   uint32_t next_tok = (n - 1 - lane) >= 0 && lane < m ? tk[n - 1 - lane] : 0;
   for (int hi = n; hi > 0; hi -= m, m = 32) {
@@ -409,7 +415,11 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
       // 32-step chain on registers only: ISETP -> SEL -> IMAD.HI -> IMAD -> SEL -> LDS -> IMAD
       uint32_t pf[32], prc[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { pf[j] = __shfl_sync(0xffffffffu, packed, j); prc[j] = __shfl_sync(0xffffffffu, rcp, j); }
+      for (int j = 0; j < 32; ++j) {
+        pf[j] = __shfl_sync(0xffffffffu, packed, j); prc[j] = __shfl_sync(0xffffffffu, rcp, j);
+        // volatile: keeps all 64 shuffles ahead of the (volatile) loads of the chain, i.e. off its critical path
+        asm volatile("" : "+r"(pf[j]), "+r"(prc[j]));
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const uint32_t f = pf[j] & 0x1FFF, tab_a = pf[j] >> 13;
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
         const bool fix = r >= f;
         const uint32_t a_lo = tab_a + 2 * r, a_hi = tab_b + 2 * r;
         uint16_t v;
-        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
         state = ((fix ? q + 1 : q) << kAnsLogTabSize) + v;
       }
     } else {
@@ -491,6 +501,8 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
       start_bit[g] = (unsigned long long)lo_bit;
     }
   }
+  __syncwarp();
+  }  // next group
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -517,8 +529,8 @@ void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t
 }
 
 void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
-                       const uint16_t* rmap, const int* num_clusters, uint32_t* out_arena, unsigned long long* start_bit,
-                       int num_groups, cudaStream_t s) {
+                       const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
+                       uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
   static bool configured = false;
   const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
                       kAnsWarps * kStageWords * 4;
@@ -527,8 +539,10 @@ void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, con
     configured = true;
   }
   ++g_kernel_launches;
-  k_ans_groups<<<(num_groups + kAnsWarps - 1) / kAnsWarps, kAnsWarps * 32, smem, s>>>(
-      tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, num_clusters, num_groups, out_arena, start_bit);
+  const int per_cta = kAnsWarps * (groups_per_warp < 1 ? 1 : groups_per_warp);
+  cudaMemsetAsync(work_counter, 0, 4, s);
+  k_ans_groups<<<(num_groups + per_cta - 1) / per_cta, kAnsWarps * 32, smem, s>>>(
+      tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, num_clusters, num_groups, work_counter, out_arena, start_bit);
 }
 
 int cluster_num_clusters_offset() { return (int)offsetof(ClusterState, num_clusters); }

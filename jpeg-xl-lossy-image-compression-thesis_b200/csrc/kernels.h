@@ -41,8 +41,8 @@ void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* 
 void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t* norm, uint16_t* rmap, void* info,
                        uint32_t* hdr_bits, uint32_t* hdr_len, cudaStream_t s);
 void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
-                       const uint16_t* rmap, const int* num_clusters, uint32_t* out_arena, unsigned long long* start_bit,
-                       int num_groups, cudaStream_t s);
+                       const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
+                       uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s);
 // K11 (k_modular.cu)
 void launch_tree_blob(int num_dc_groups, uint32_t* tree_words, uint32_t* tree_bits, cudaStream_t s);
 void launch_mod_ranks(const uint8_t* acs, const int32_t* raw_qf, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
@@ -61,7 +61,8 @@ void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32
 void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
                      const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
                      Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
-                     unsigned long long* out_info, cudaStream_t s);
+                     unsigned long long* out_info, const QuantDev* qd, const uint32_t* token_counts, const int* num_clusters,
+                     cudaStream_t s);
 void launch_assemble(const Section* sections, int num_sections, const uint32_t* lf_words, const uint32_t* mod_words,
                      const uint32_t* hf_words, const uint32_t* group_arena, uint32_t* out_words,
                      const unsigned long long* out_info, cudaStream_t s);

@@ -114,6 +114,13 @@ def load_library() -> ctypes.CDLL:
     lib.jxlb200_encode_batch.restype = ctypes.c_int
     lib.jxlb200_encode_batch.argtypes = [vp, ctypes.POINTER(_Image), ctypes.POINTER(_Params), ctypes.c_size_t,
                                          u8pp, szp, ctypes.POINTER(_Stats)]
+    lib.jxlb200_encode_batch_device.restype = ctypes.c_int
+    lib.jxlb200_encode_batch_device.argtypes = [vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint32),
+                                                ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t),
+                                                ctypes.POINTER(_Params), ctypes.c_size_t, ctypes.POINTER(_Stats),
+                                                ctypes.POINTER(ctypes.c_float)]
+    lib.jxlb200_set_pipelines.restype = ctypes.c_int
+    lib.jxlb200_set_pipelines.argtypes = [vp, ctypes.c_int]
     lib.jxlb200_free.argtypes = [vp]
     lib.jxlb200_dump.restype = ctypes.c_int64
     lib.jxlb200_dump.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
@@ -192,6 +199,58 @@ class Encoder:
         if rc != 0:
             raise EncodeError(self._err())
         return Stats._from_c(st)
+
+    def set_pipelines(self, n: int) -> None:
+        """How many images the batch calls keep in flight (one CUDA stream + arenas each)."""
+        if self._lib.jxlb200_set_pipelines(self._ctx, n) != 0:
+            raise EncodeError(self._err())
+
+    def encode_batch(self, images, distance=1.0, effort: int = 7, proposal: int = PROPOSAL_NONE, flags: int = 0):
+        """The per-image loop of ``JXLCompressionBenchmark::run`` (benchmark.rs:637-660) as one call:
+        ``images`` is a list of (h, w, 3) uint8 arrays (pinned memory is copied without staging);
+        ``distance`` may be a scalar or one value per image.  Returns ([bytes], [Stats])."""
+        n = len(images)
+        dist = list(distance) if hasattr(distance, "__len__") else [distance] * n
+        imgs = (_Image * n)()
+        pars = (_Params * n)()
+        keep = []
+        for i, im in enumerate(images):
+            if im.dtype != np.uint8 or im.ndim != 3 or im.shape[2] != 3:
+                raise EncodeError("image must be (h, w, 3) uint8")
+            if im.strides[2] != 1 or im.strides[1] != 3:
+                im = np.ascontiguousarray(im)
+            keep.append(im)
+            imgs[i] = _Image(im.ctypes.data, im.shape[1], im.shape[0], im.strides[0])
+            pars[i] = _Params(dist[i], effort, proposal, flags)
+        outs = (ctypes.POINTER(ctypes.c_uint8) * n)()
+        lens = (ctypes.c_size_t * n)()
+        sts = (_Stats * n)()
+        rc = self._lib.jxlb200_encode_batch(self._ctx, imgs, pars, n, outs, lens, sts)
+        if rc != 0:
+            raise EncodeError(self._err())
+        data = []
+        for i in range(n):
+            data.append(ctypes.string_at(outs[i], lens[i]))
+            self._lib.jxlb200_free(outs[i])
+        return data, [Stats._from_c(s) for s in sts]
+
+    def encode_batch_device(self, d_ptrs, width: int, height: int, stride: int, distance=1.0, effort: int = 7,
+                            proposal: int = PROPOSAL_NONE, flags: int = 0):
+        """Batch over RGB8 images resident in device memory (``d_ptrs`` = device addresses).  Returns
+        ([Stats], device_ms) where device_ms is the CUDA-event time of the whole batch."""
+        n = len(d_ptrs)
+        dist = list(distance) if hasattr(distance, "__len__") else [distance] * n
+        ptrs = (ctypes.c_void_p * n)(*d_ptrs)
+        ws = (ctypes.c_uint32 * n)(*([width] * n))
+        hs = (ctypes.c_uint32 * n)(*([height] * n))
+        ss = (ctypes.c_size_t * n)(*([stride] * n))
+        pars = (_Params * n)(*[_Params(dist[i], effort, proposal, flags) for i in range(n)])
+        sts = (_Stats * n)()
+        ms = ctypes.c_float(0.0)
+        rc = self._lib.jxlb200_encode_batch_device(self._ctx, ptrs, ws, hs, ss, pars, n, sts, ctypes.byref(ms))
+        if rc != 0:
+            raise EncodeError(self._err())
+        return [Stats._from_c(s) for s in sts], float(ms.value)
 
     def fetch(self) -> bytes:
         out = ctypes.POINTER(ctypes.c_uint8)()

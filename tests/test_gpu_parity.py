@@ -152,3 +152,23 @@ def test_full_size_properties(pkg, oracle, encoder):
     assert np.array_equal(dec.dump("dc_quant"), encoder.dump("dc_quant"))
     assert np.array_equal(_valid_coeffs(dec.dump("coeffs"), d), _valid_coeffs(encoder.dump("coeffs"), d))
     assert st.num_groups == 135 and st.num_dc_groups == 4 and 0.2 < st.bpp < 4.0
+
+
+def test_batch_matches_single(pkg, oracle, encoder):
+    """jxlb200_encode_batch keeps several images in flight on separate streams; every codestream must equal the
+    one-at-a-time result (and so the oracle's)."""
+    imgs = [pkg.synth_image(200 + 24 * i, 136 + 8 * i, 40 + i) for i in range(7)]
+    dists = [0.5, 1.0, 1.5, 2.0, 2.5, 3.0, 1.0]
+    encoder.set_pipelines(3)
+    datas, sts = encoder.encode_batch(imgs, dists, 7, 0, 1)
+    for im, d, data, st in zip(imgs, dists, datas, sts):
+        single, _ = encoder.encode(im, d, 7, 0, 1)
+        assert data == single
+        assert np.array_equal(np.frombuffer(data, dtype=np.uint8), oracle.encode(im, d, 7, 0, 1).dump("codestream"))
+        assert st.codestream_bytes == len(data)
+    import torch
+    d_imgs = [torch.from_numpy(imgs[0]).cuda() for _ in range(5)]
+    sts, ms = encoder.encode_batch_device([t.data_ptr() for t in d_imgs], imgs[0].shape[1], imgs[0].shape[0],
+                                          3 * imgs[0].shape[1], 0.5, 7, 0, 1)
+    assert ms > 0 and all(s.codestream_bytes == len(datas[0]) for s in sts)
+    encoder.set_pipelines(4)

@@ -67,6 +67,19 @@ bool Encoder::Init(int device, std::string* err) {
     *err = "alloc"; return false;
   }
   CUDA_OK(cudaMallocHost(&h_out_info_, 8 * sizeof(unsigned long long)));
+  {
+    // inverse natural coefficient orders of the order classes the search can emit
+    static const int rep[13] = {0, 3, 4, 5, 6, 8, 10, -1, -1, -1, -1, -1, -1};
+    for (int o = 0; o < 13; ++o) {
+      if (rep[o] < 0) continue;
+      std::vector<uint16_t> order;
+      host_natural_order(rep[o], &order);
+      std::vector<uint16_t> inv(order.size());
+      for (size_t k = 0; k < order.size(); ++k) inv[order[k]] = (uint16_t)k;
+      if (!d_inv_order_[o].Reserve(inv.size())) { *err = "alloc"; return false; }
+      CUDA_OK(cudaMemcpy(d_inv_order_[o].p, inv.data(), inv.size() * 2, cudaMemcpyHostToDevice));
+    }
+  }
   if (!d_cvx_.Reserve(27) || !d_cvy_.Reserve(27) || !d_q_.Reserve(1)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_cvx_.p, kCoveredX, 27, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d_cvy_.p, kCoveredY, 27, cudaMemcpyHostToDevice));
@@ -80,6 +93,7 @@ void Encoder::Destroy() {
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); }
   d_izz8_.Release(); d_cvx_.Release(); d_cvy_.Release();
+  for (int o = 0; o < 13; ++o) d_inv_order_[o].Release();
   d_rgb_.Release(); d_xyb_.Release(); d_mask1x1_.Release(); d_pre_.Release(); d_qf_.Release(); d_mask_.Release();
   d_homog_.Release(); d_acs_entropy_.Release(); d_acs_.Release(); d_raw_qf_.Release(); d_cmap_.Release();
   d_coeffs_.Release(); d_dc_quant_.Release(); d_nzeros_.Release(); d_nzcount_.Release(); d_lastk_.Release(); d_q_.Release();
@@ -228,16 +242,41 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   // K4: homogeneity map (the thesis' proposals)
   launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[4], stream_));
-  // K6: AC strategy (fixed DCT8 until the search kernel lands)
-  CUDA_OK(cudaMemsetAsync(d_acs_.p, 0x80, nblk, stream_));
-  CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));
+  // K6: AC strategy search (+ the proposals' hooks); DCT8 everywhere when fixed or below effort 5
+  const bool search = !(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5;
   CUDA_OK(cudaMemsetAsync(d_cmap_.p, 0, (size_t)2 * fd.txs * fd.tys, stream_));
+  AcsTables tables;
+  for (int k = 0; k < 17; ++k) { tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; }
+  if (search) {
+    AcsParams ap;
+    const float ratio = (p.distance + 0.1373f) / 1.1373f;
+    ap.info_loss_multiplier = 1.2f * powf(ratio, 0.33677806662454718f);
+    ap.zeros_mul = 9.3089171683409026f * powf(ratio, 0.50990926717963703f);
+    ap.cost_delta = 10.833273317067883f * powf(ratio, 0.36702940662370243f);
+    ap.distance = p.distance;
+    ap.mul8x8 = 1.0f - 0.4f / (p.distance + 1.4f);
+    ap.cmap_x = 0.0f; ap.cmap_b = 1.0f;   // colour correlation map is the default (all tiles 0)
+    ap.partitioning = p.proposal == JXLB200_PROPOSAL_PARTITIONING || p.proposal == JXLB200_PROPOSAL_COMBINED;
+    ap.factored_entropy = p.proposal == JXLB200_PROPOSAL_FACTORED_ENTROPY || p.proposal == JXLB200_PROPOSAL_COMBINED;
+    launch_acs(X, Y, B, d_mask1x1_.p, d_qf_.p, d_homog_.p, fd, ap, tables, d_acs_.p, d_acs_entropy_.p, stream_);
+  } else {
+    CUDA_OK(cudaMemsetAsync(d_acs_.p, 0x80, nblk, stream_));
+    CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));
+  }
   launch_raw_qf(d_qf_.p, d_acs_.p, fd, d_q_.p, d_cvx_.p, d_cvy_.p, d_raw_qf_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[5], stream_));
   // K7: transform + quantise
-  launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
-                    b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
-                    d_nzcount_.p, d_lastk_.p, stream_);
+  if (search) {
+    const uint16_t* inv_order[13];
+    for (int o = 0; o < 13; ++o) inv_order[o] = d_inv_order_[o].p;
+    launch_coeff_general(X, Y, B, d_acs_.p, fd, d_q_.p, tables, inv_order, d_cmap_.p, x_qm_mul_, b_qm_mul_,
+                         p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
+                         stream_);
+  } else {
+    launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
+                      b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
+                      d_nzcount_.p, d_lastk_.p, stream_);
+  }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
   // K8: tokens + per-context histograms
   CUDA_OK(cudaMemsetAsync(d_hist_.p, 0, (size_t)kNumAcContexts * kAcAlphabet * 4, stream_));

@@ -65,6 +65,7 @@ class Encoder {
   DevBuf<float> d_weights_[17];
   DevBuf<float> d_dequant_[17];
   DevBuf<uint8_t> d_izz8_;        // DCT8: position -> scan index
+  DevBuf<uint16_t> d_inv_order_[13];  // per order class: coefficient position -> scan index
   DevBuf<uint8_t> d_cvx_, d_cvy_;
   // per-frame arenas
   DevBuf<uint8_t> d_rgb_;

@@ -24,6 +24,19 @@ void launch_dct8_quant(const float* x, const float* y, const float* b, const Fra
                        float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
                        uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
 
+// K6 (k_acs.cu) / K7 general (k_coeff.cu)
+struct AcsParams {
+  float info_loss_multiplier, zeros_mul, cost_delta, distance, mul8x8, cmap_x, cmap_b;
+  int factored_entropy, partitioning;   // H9 / H8 hooks of the thesis' proposals
+};
+struct AcsTables { const float* w[17]; const float* dq[17]; };   // quantisation weights / their inverses per table kind
+void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,
+                const FrameDim& fd, const AcsParams& P, const AcsTables& T, uint8_t* acs, float* est, cudaStream_t s);
+void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
+                          const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
+                          float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
+                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
+
 // ---- entropy stage -------------------------------------------------------------------------
 // one 2048x2048 DC group: rectangle in blocks, its 64x64-tile rectangle, first element / first block slot
 struct DcGroupInfo { int x0, y0, w, h, tw, th; uint32_t elem_base; uint32_t block_base; };

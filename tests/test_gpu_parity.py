@@ -172,3 +172,57 @@ def test_batch_matches_single(pkg, oracle, encoder):
                                           3 * imgs[0].shape[1], 0.5, 7, 0, 1)
     assert ms > 0 and all(s.codestream_bytes == len(datas[0]) for s in sts)
     encoder.set_pipelines(4)
+
+
+# ---------------------------------------------------------------------------------------------
+# AC-strategy search (U4) with the proposals' hooks (H8 / H9 / H10) and the general transform +
+# quantise kernel: strategy map, entropy estimates, coefficients and the whole codestream bit-exact.
+ACS_STAGES = ("acs", "acs_entropy", "raw_qf", "dc_quant", "nzeros", "coeffs") + ENTROPY_STAGES
+
+
+def compare_full(pkg, oracle, enc, img, distance, effort, proposal):
+    data, st = enc.encode(img, distance, effort, proposal, 0)
+    ora = oracle.encode(img, distance, effort, proposal, 0)
+    assert ora.error == ""
+    d = pkg.frame_dims(img.shape[1], img.shape[0])
+    for stg in ACS_STAGES:
+        a, b = enc.dump(stg), ora.dump(stg)
+        assert a.shape == b.shape, stg
+        if stg == "coeffs":
+            a, b = _valid_coeffs(a, d), _valid_coeffs(b, d)
+        if stg == "acs_entropy":
+            same = (a == b) | (np.isnan(a) & np.isnan(b))
+        else:
+            same = a == b
+        if not same.all():
+            bad = np.flatnonzero(~same.reshape(-1))
+            raise AssertionError(f"{stg}: {bad.size} mismatches, first at {bad[:8]}: {a.reshape(-1)[bad[:8]]} vs {b.reshape(-1)[bad[:8]]}")
+    dec = oracle.decode(data)
+    assert dec.error == "", dec.error
+    assert np.array_equal(dec.dump("acs"), enc.dump("acs"))
+    return st
+
+
+@pytest.mark.parametrize("proposal", [0, 1, 2, 3])
+def test_acs_parity_proposals(pkg, oracle, encoder, proposal):
+    st = compare_full(pkg, oracle, encoder, pkg.synth_image(512, 384, 3), 1.0, 7, proposal)
+
+
+@pytest.mark.parametrize("w,h", [(64, 64), (8, 8), (1, 1), (257, 9), (264, 300), (100, 60)])
+def test_acs_parity_sizes(pkg, oracle, encoder, w, h):
+    compare_full(pkg, oracle, encoder, pkg.synth_image(w, h, 2 * w + h), 1.0, 7, 3)
+
+
+@pytest.mark.parametrize("distance", [0.5, 2.0, 3.0, 4.5, 8.0, 12.0])
+def test_acs_parity_distances(pkg, oracle, encoder, distance):
+    compare_full(pkg, oracle, encoder, pkg.synth_image(320, 256, 17), distance, 7, 3)
+
+
+def test_acs_parity_extremes(pkg, oracle, encoder):
+    for fill in (0, 255):   # all-black: 0/0 -> NaN ratios (H7), NaN entropy under H9
+        compare_full(pkg, oracle, encoder, np.full((64, 96, 3), fill, dtype=np.uint8), 1.0, 7, 3)
+    rng = np.random.default_rng(5)
+    compare_full(pkg, oracle, encoder, rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8), 1.0, 7, 3)
+    img = pkg.synth_image(256, 256, 9)
+    compare_full(pkg, oracle, encoder, img, 1.0, 4, 3)   # effort < 5: no search
+    compare_full(pkg, oracle, encoder, img, 1.0, 9, 1)

@@ -226,3 +226,14 @@ def test_acs_parity_extremes(pkg, oracle, encoder):
     img = pkg.synth_image(256, 256, 9)
     compare_full(pkg, oracle, encoder, img, 1.0, 4, 3)   # effort < 5: no search
     compare_full(pkg, oracle, encoder, img, 1.0, 9, 1)
+
+
+def test_codestream_pins_gpu(pkg, encoder):
+    """The committed golden pins (tests/golden/codestream_pins.json) hold for the CUDA path as well."""
+    import hashlib, json, os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "codestream_pins.json")) as f:
+        pins = json.load(f)
+    for p in pins:
+        data, _ = encoder.encode(pkg.synth_image(p["w"], p["h"], p["index"]), p["distance"], p["effort"], p["proposal"], p["flags"])
+        assert len(data) == p["bytes"] and hashlib.sha256(data).hexdigest() == p["sha256"], p
+        assert hashlib.sha256(encoder.dump("acs").tobytes()).hexdigest() == p["acs_sha256"], p

@@ -74,3 +74,45 @@ def test_corrupt_stream_rejected(pkg, oracle):
                 or not np.array_equal(d.dump("dc_quant"), oracle.decode(cs.tobytes()).dump("dc_quant")):
             flips += 1
     assert flips >= 30   # nearly every bit flip is either rejected or changes the decoded integers
+
+
+@pytest.mark.parametrize("proposal", [0, 1, 2, 3])
+def test_roundtrip_with_search(pkg, oracle, proposal):
+    """Full AC-strategy search (all emitted transform sizes) + the proposals' hooks: the codestream still
+    decodes to exactly what was coded, and the hooks change the partition."""
+    img = pkg.synth_image(256, 192, 31)
+    f = oracle.encode(img, 1.0, 7, proposal, 0)
+    assert f.error == ""
+    d = oracle.decode(f.dump("codestream").tobytes())
+    assert d.error == "", d.error
+    for st in LOSSLESS_STAGES:
+        assert np.array_equal(f.dump(st), d.dump(st)), st
+    acs = f.dump("acs")
+    first = acs[acs >= 128] & 0x7F
+    assert set(np.unique(first)) <= {0, 3, 4, 5, 6, 7, 10, 11, 12, 13}
+    assert len(set(np.unique(first))) >= 4                     # the search really mixes transform sizes
+    base = oracle.encode(img, 1.0, 7, 0, 0).dump("acs")
+    if proposal:
+        assert not np.array_equal(acs, base)
+
+
+def test_search_effort_gate_and_size(pkg, oracle):
+    img = pkg.synth_image(256, 256, 3)
+    fixed = oracle.encode(img, 1.0, 7, 0, 1)
+    low = oracle.encode(img, 1.0, 4, 0, 0)                     # below effort 5 ProcessRectACS returns early
+    assert np.all((low.dump("acs") & 0x7F) == 0)
+    full = oracle.encode(img, 1.0, 7, 0, 0)
+    assert full.dump("codestream").size < fixed.dump("codestream").size   # variable-size transforms pay off
+
+
+def test_partition_override_keeps_estimate(pkg, oracle):
+    """H8: the override replaces DCT8 winners only and does not recompute their entropy estimate."""
+    img = pkg.synth_image(128, 128, 12)
+    a = oracle.encode(img, 1.0, 4, 0, 0)   # effort 4 = no search; compare level-8 semantics through effort 7 below
+    f0 = oracle.encode(img, 1.0, 7, 0, 0)
+    f1 = oracle.encode(img, 1.0, 7, 1, 0)
+    acs0, acs1 = f0.dump("acs"), f1.dump("acs")
+    changed = np.flatnonzero(acs0 != acs1)
+    # every strategy the partitioning proposal introduces is one of its three outputs or a merge consequence
+    assert changed.size > 0
+    assert set(np.unique(acs1[changed] & 0x7F)) <= {0, 3, 12, 13, 4, 5, 6, 7, 10, 11}

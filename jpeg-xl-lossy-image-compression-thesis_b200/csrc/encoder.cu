@@ -240,7 +240,9 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   launch_quant_params(d_qf_.p, nblk, host_initial_quant_dc(p.distance), d_q_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[3], stream_));
   // K4: homogeneity map (the thesis' proposals)
-  launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
+  // (only the proposals read it: H8 / H9; the unpatched encoder has no use for the map)
+  if (p.proposal != JXLB200_PROPOSAL_NONE) launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
+  else CUDA_OK(cudaMemsetAsync(d_homog_.p, 0, 3 * nblk * 4, stream_));
   CUDA_OK(cudaEventRecord(ev_[4], stream_));
   // K6: AC strategy search (+ the proposals' hooks); DCT8 everywhere when fixed or below effort 5
   const bool search = !(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5;

@@ -228,20 +228,29 @@ __device__ uint32_t radix_select(const float* __restrict__ v, size_t n, size_t k
     __syncthreads();
     // the field is narrow-ranged, so most values share a digit: aggregate equal digits inside the
     // warp (match.any) and let one lane per distinct digit do the shared-memory atomic
-    for (size_t i0 = 0; i0 < n; i0 += blockDim.x) {
-      const size_t i = i0 + threadIdx.x;
-      bool match = false;
-      uint32_t digit = 0;
-      if (i < n) {
-        const float f = kDeviation ? fabsf(v[i] - center) : v[i];
-        const uint32_t u = __float_as_uint(f);
-        match = done_bits == 0 ? true : ((u >> (32 - done_bits)) == (prefix >> (32 - done_bits)));
-        digit = (u >> shifts[pass]) & (nb - 1);
+    for (size_t i0 = 0; i0 < n; i0 += (size_t)blockDim.x * 8) {
+      float vals[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {       // eight independent loads in flight before any of them is consumed
+        const size_t i = i0 + (size_t)u * blockDim.x + threadIdx.x;
+        vals[u] = i < n ? v[i] : 0.0f;
       }
-      const unsigned part = __ballot_sync(0xffffffffu, match);
-      if (match) {
-        const unsigned peers = __match_any_sync(part, digit);
-        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const size_t i = i0 + (size_t)u * blockDim.x + threadIdx.x;
+        bool match = false;
+        uint32_t digit = 0;
+        if (i < n) {
+          const float f = kDeviation ? fabsf(vals[u] - center) : vals[u];
+          const uint32_t uu = __float_as_uint(f);
+          match = done_bits == 0 ? true : ((uu >> (32 - done_bits)) == (prefix >> (32 - done_bits)));
+          digit = (uu >> shifts[pass]) & (nb - 1);
+        }
+        const unsigned part = __ballot_sync(0xffffffffu, match);
+        if (match) {
+          const unsigned peers = __match_any_sync(part, digit);
+          if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+        }
       }
     }
     __syncthreads();

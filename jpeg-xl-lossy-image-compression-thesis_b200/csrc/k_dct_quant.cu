@@ -117,7 +117,7 @@ __device__ __forceinline__ void quantize_row(const float in[8], const float* w, 
 
 constexpr int kRowsPerCta = 4;  // block rows processed by one CTA (amortises table staging)
 
-__global__ void __launch_bounds__(256) k_dct8_quant(const float* __restrict__ X, const float* __restrict__ Y,
+__global__ void __launch_bounds__(256, 3) k_dct8_quant(const float* __restrict__ X, const float* __restrict__ Y,
                                                     const float* __restrict__ B, FrameDim fd,
                                                     const QuantDev* __restrict__ qd, const float* __restrict__ weights,
                                                     const float* __restrict__ dequant_y, const uint8_t* __restrict__ izz,

@@ -37,21 +37,28 @@ __constant__ uint8_t c_nnz_ctx[64] = {0,   0,   31,  62,  62,  93,  93,  93,  93
                                       206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
 
 // ------------------------------------------------------------------------------------------ K8
-__global__ void __launch_bounds__(1024) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
-                                                   const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
-                                                   const int16_t* __restrict__ coeffs, FrameDim fd,
-                                                   uint32_t* __restrict__ tokens, uint32_t* __restrict__ token_counts,
-                                                   uint32_t* __restrict__ hist) {
+constexpr int kTokSplit = 8;   // CTAs per AC group (each recomputes the group's scan, emits 1/8 of the entries)
+
+__global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
+                                                  const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
+                                                  const int16_t* __restrict__ coeffs, FrameDim fd,
+                                                  uint32_t* __restrict__ tokens, uint32_t* __restrict__ token_counts,
+                                                  uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_off[3072 + 1];
-  __shared__ uint32_t s_warp[32];
-  const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ uint32_t s_warp[8];
+  // CTA-private counters of symbols 0 and 1 of every context: those bins take most of the increments
+  // (zero coefficients, +-1) and a few of them are so hot that global atomics on them serialise in L2
+  extern __shared__ uint32_t s_hot[];   // [2][kNumAcContexts]
+  const int g = blockIdx.x, part = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int i = t; i < 2 * kNumAcContexts; i += 256) s_hot[i] = 0;
   const int gx0 = (g % fd.gxs) * 32, gy0 = (g / fd.gxs) * 32;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
-  // ---- token count per (block, slot): thread t = block t of the group
-  uint32_t cnt[3];
+  // ---- token count per (block, slot): 12 consecutive entries per thread = 4 blocks
+  uint32_t cnt[12];
   uint32_t sum = 0;
-  {
-    const int lx = t & 31, ly = t >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int blk = t * 4 + i, lx = blk & 31, ly = blk >> 5;
     const int bx = gx0 + lx, by = gy0 + ly;
     const bool inside = bx < fd.bxs && by < fd.bys;
     uint8_t a = 0;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(1024) k_tokenize(const uint8_t* __restrict__ a
         const int nz = nzcount[bi];
         v = 1 + (nz ? (uint32_t)(lastk[bi] - n + 1) : 0u);
       }
-      cnt[slot] = v;
+      cnt[i * 3 + slot] = v;
       sum += v;
     }
   }
@@ -80,66 +87,92 @@ __global__ void __launch_bounds__(1024) k_tokenize(const uint8_t* __restrict__ a
   uint32_t base = incl - sum;
   for (int w = 0; w < warp; ++w) base += s_warp[w];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { s_off[t * 3 + i] = base; base += cnt[i]; }
-  if (t == 1023) { s_off[3072] = base; token_counts[g] = base; }
+  for (int i = 0; i < 12; ++i) { s_off[t * 12 + i] = base; base += cnt[i]; }
+  if (t == 255) { s_off[3072] = base; if (part == 0) token_counts[g] = base; }
   __syncthreads();
-  // ---- emit: one warp per (block, slot)
+  // ---- emit: this CTA's slice of the entries; a warp takes 32 entries at a time, every lane
+  // prefetching the metadata of one of them, then the warp walks the 32 entries together
   uint32_t* out = tokens + (size_t)g * kTokensPerGroupMax;
-  for (int e = warp; e < 3072; e += 32) {
-    const uint32_t off = s_off[e];
-    const uint32_t count = s_off[e + 1] - off;
-    if (count == 0) continue;
-    const int blk = e / 3, slot = e - blk * 3;
-    const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
-    const int lx = blk & 31, ly = blk >> 5, bx = gx0 + lx, by = gy0 + ly;
-    const int s = acs[(size_t)by * fd.bxs + bx] & 0x7f;
-    const int cx = c_covered_x[s], cy = c_covered_y[s], n = cx * cy, size = n * 64;
-    const int log2n = 31 - __clz(n);
-    const int block_ctx = c_block_ctx_map[(c < 2 ? c ^ 1 : 2) * kNumOrders + c_strategy_order[s]];
-    const uint8_t* nzp = nzeros + (size_t)c * nblk;
-    const size_t bi = (size_t)by * fd.bxs + bx;
-    int nz = nzcount[(size_t)c * nblk + bi];
-    if (lane == 0) {
-      int pred;
-      if (lx == 0) pred = ly == 0 ? 32 : nzp[bi - fd.bxs];
-      else if (ly == 0) pred = nzp[bi - 1];
-      else pred = (nzp[bi - fd.bxs] + nzp[bi - 1] + 1) >> 1;
-      const int p = pred >= 64 ? 64 : pred;
-      const int bucket = p < 8 ? p : 4 + (p >> 1);
-      const uint32_t ctx = (uint32_t)(bucket * kNumBlockCtx + block_ctx);
-      out[off] = (ctx << 16) | (uint32_t)nz;
-      uint32_t tok, nb, bits;
-      hybrid_encode((uint32_t)nz, tok, nb, bits);
-      atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
-    }
-    if (count == 1) continue;
-    const int histo_offset = kNumBlockCtx * kNonZeroBuckets + kZeroDensityContextCount * block_ctx;
-    int prev_carry = nz > size / 16 ? 0 : 1;
-    const int last = n + (int)count - 2;  // scan position of the last non-zero coefficient
-    for (int k0 = n; k0 <= last; k0 += 32) {
-      const int k = k0 + lane;
-      int coef = 0;
-      if (k <= last) {
-        const int j = k >> 6;
-        const int jx = j % cx, jy = j / cx;
-        const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
-        coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, coef != 0);
-      const int nz_here = nz - __popc(mask & ((1u << lane) - 1));
-      const int prev = lane == 0 ? prev_carry : (int)((mask >> (lane - 1)) & 1);
-      if (k <= last) {
-        const int nzl = (nz_here + n - 1) >> log2n;
-        const uint32_t ctx = (uint32_t)(histo_offset + (c_nnz_ctx[nzl] + c_freq_ctx[k >> log2n]) * 2 + prev);
-        const uint32_t v = pack_signed(coef);
-        out[off + 1 + (k - n)] = (ctx << 16) | v;
+  constexpr int kPerCta = 3072 / kTokSplit;          // 384
+  constexpr int kPerWarp = kPerCta / 8;              // 48
+  const int e_begin = part * kPerCta + warp * kPerWarp;
+  for (int e0 = e_begin; e0 < e_begin + kPerWarp; e0 += 32) {
+    const int e = e0 + lane;
+    uint32_t m_off = 0, m_count = 0, m_nztok = 0, m_misc = 0;   // misc: s | block_ctx << 8 | nz << 16
+    if (e < e_begin + kPerWarp) {
+      m_off = s_off[e];
+      m_count = s_off[e + 1] - m_off;
+      if (m_count) {
+        const int blk = e / 3, slot = e - blk * 3;
+        const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
+        const int lx = blk & 31, ly = blk >> 5, bx = gx0 + lx, by = gy0 + ly;
+        const size_t bi = (size_t)by * fd.bxs + bx;
+        const int s = acs[bi] & 0x7f;
+        const int block_ctx = c_block_ctx_map[(c < 2 ? c ^ 1 : 2) * kNumOrders + c_strategy_order[s]];
+        const uint8_t* nzp = nzeros + (size_t)c * nblk;
+        const int nz = nzcount[(size_t)c * nblk + bi];
+        int pred;
+        if (lx == 0) pred = ly == 0 ? 32 : nzp[bi - fd.bxs];
+        else if (ly == 0) pred = nzp[bi - 1];
+        else pred = (nzp[bi - fd.bxs] + nzp[bi - 1] + 1) >> 1;
+        const int p = pred >= 64 ? 64 : pred;
+        const int bucket = p < 8 ? p : 4 + (p >> 1);
+        const uint32_t ctx = (uint32_t)(bucket * kNumBlockCtx + block_ctx);
+        m_nztok = (ctx << 16) | (uint32_t)nz;
+        m_misc = (uint32_t)s | ((uint32_t)block_ctx << 8) | ((uint32_t)nz << 16);
+        out[m_off] = m_nztok;
         uint32_t tok, nb, bits;
-        hybrid_encode(v, tok, nb, bits);
-        atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+        hybrid_encode((uint32_t)nz, tok, nb, bits);
+        if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
       }
-      nz -= __popc(mask);
-      prev_carry = (int)(mask >> 31);
     }
+    unsigned todo = __ballot_sync(0xffffffffu, m_count > 1);
+    while (todo) {
+      const int j = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t off = __shfl_sync(0xffffffffu, m_off, j);
+      const uint32_t count = __shfl_sync(0xffffffffu, m_count, j);
+      const uint32_t misc = __shfl_sync(0xffffffffu, m_misc, j);
+      const int ee = e0 + j;
+      const int blk = ee / 3, slot = ee - blk * 3;
+      const int lx = blk & 31, ly = blk >> 5;
+      const int s = misc & 0xff, block_ctx = (misc >> 8) & 0xff;
+      int nz = (int)(misc >> 16);
+      const int cx = c_covered_x[s], cy = c_covered_y[s], n = cx * cy, size = n * 64;
+      const int log2n = 31 - __clz(n);
+      const int histo_offset = kNumBlockCtx * kNonZeroBuckets + kZeroDensityContextCount * block_ctx;
+      int prev_carry = nz > size / 16 ? 0 : 1;
+      const int last = n + (int)count - 2;  // scan position of the last non-zero coefficient
+      for (int k0 = n; k0 <= last; k0 += 32) {
+        const int k = k0 + lane;
+        int coef = 0;
+        if (k <= last) {
+          const int jj = k >> 6;
+          const int jx = jj % cx, jy = jj / cx;
+          const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
+          coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, coef != 0);
+        const int nz_here = nz - __popc(mask & ((1u << lane) - 1));
+        const int prev = lane == 0 ? prev_carry : (int)((mask >> (lane - 1)) & 1);
+        if (k <= last) {
+          const int nzl = (nz_here + n - 1) >> log2n;
+          const uint32_t ctx = (uint32_t)(histo_offset + (c_nnz_ctx[nzl] + c_freq_ctx[k >> log2n]) * 2 + prev);
+          const uint32_t v = pack_signed(coef);
+          out[off + 1 + (k - n)] = (ctx << 16) | v;
+          uint32_t tok, nb, bits;
+          hybrid_encode(v, tok, nb, bits);
+          if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+        }
+        nz -= __popc(mask);
+        prev_carry = (int)(mask >> 31);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < 2 * kNumAcContexts; i += 256) {
+    const uint32_t v = s_hot[i];
+    if (v) { const int tok = i >= kNumAcContexts, ctx = i - tok * kNumAcContexts; atomicAdd(&hist[ctx * kAcAlphabet + tok], v); }
   }
 }
 
@@ -511,8 +544,13 @@ size_t cluster_state_bytes() { return sizeof(ClusterState); }
 void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* nzcount, const uint16_t* lastk,
                      const int16_t* coeffs, const FrameDim& fd, uint32_t* tokens, uint32_t* token_counts, uint32_t* hist,
                      cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kNumAcContexts * sizeof(uint32_t)));
+    configured = true;
+  }
   ++g_kernel_launches;
-  k_tokenize<<<fd.num_groups, 1024, 0, s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
+  k_tokenize<<<dim3(fd.num_groups, kTokSplit), 256, 2 * kNumAcContexts * sizeof(uint32_t), s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
 }
 
 void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,

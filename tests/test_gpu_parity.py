@@ -45,13 +45,13 @@ def compare_all(pkg, oracle, enc, img, distance, effort, proposal, flags, stages
 @pytest.mark.parametrize("flags", [1, 3])
 def test_stage_parity_dct8(pkg, oracle, encoder, w, h, flags):
     img = pkg.synth_image(w, h, w * 7 + h)
-    compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, flags, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+    compare_all(pkg, oracle, encoder, img, 1.0, 7, 3, flags, FLOAT_STAGES + INT_STAGES + ("coeffs",))
 
 
 @pytest.mark.parametrize("distance", [0.5, 1.0, 1.5, 3.0, 8.0, 14.0])
 def test_stage_parity_distances(pkg, oracle, encoder, distance):
     img = pkg.synth_image(320, 256, 11)
-    compare_all(pkg, oracle, encoder, img, distance, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+    compare_all(pkg, oracle, encoder, img, distance, 7, 3, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
 
 
 @pytest.mark.parametrize("effort", [3, 5, 9])
@@ -63,10 +63,10 @@ def test_stage_parity_efforts(pkg, oracle, encoder, effort):
 def test_extreme_images(pkg, oracle, encoder):
     for fill in (0, 255):
         img = np.full((64, 72, 3), fill, dtype=np.uint8)
-        compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+        compare_all(pkg, oracle, encoder, img, 1.0, 7, 3, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
     rng = np.random.default_rng(1)
     img = rng.integers(0, 256, size=(72, 96, 3), dtype=np.uint8)
-    compare_all(pkg, oracle, encoder, img, 1.0, 7, 0, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
+    compare_all(pkg, oracle, encoder, img, 1.0, 7, 3, 1, FLOAT_STAGES + INT_STAGES + ("coeffs",))
 
 
 def test_error_behaviour(pkg, encoder):

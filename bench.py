@@ -257,13 +257,12 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    if world > 1:
-        t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s = float(t[0]), float(t[1])
-        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(lt)
-        launches = int(lt[0])
+    # per-rank statistics -> job totals (SUM of counters, MAX of times): the only communication of the job
+    job = pkg.gather_stats(pkg.ShardStats(images=B * args.steps, pixels=B * args.steps * w * h,
+                                          codestream_bytes=out_bytes, device_ms=total_ms, kernel_launches=launches),
+                           device="cuda")
+    job_e2e = pkg.gather_stats(pkg.ShardStats(device_ms=e2e_s * 1e3), device="cuda")
+    total_ms, e2e_s, launches, out_bytes = job.max_ms, job_e2e.max_ms / 1e3, job.kernel_launches, job.codestream_bytes // world
 
     if rank == 0:
         ms_per_step = total_ms / args.steps

@@ -14,11 +14,14 @@
 
 namespace jxlb {
 
-constexpr int kCoeffWarps = 4;
+#ifndef JXLB_COEFF_WARPS
+#define JXLB_COEFF_WARPS 4
+#endif
+constexpr int kCoeffWarps = JXLB_COEFF_WARPS;
 
 struct CoeffShared {
   float px[3][32 * kTPitch];
-  float buf[kCoeffWarps][4][32 * kTPitch];   // per warp: X, Y, B coefficient rows + scratch / quantised Y
+  float buf[kCoeffWarps][3][32 * kTPitch];   // per warp: X, Y, B coefficient rows (transforms and quantisation work in place)
 };
 
 __device__ __forceinline__ float quant_bias(int c, int q) {
@@ -227,26 +230,31 @@ struct CoeffArgs {
   uint16_t* lastk;
 };
 
+// One lane group (GS = max(R, C) lanes) per transform, 32 / GS transforms side by side in a warp.
+// Inactive groups run the same instruction stream on the tile origin with every store suppressed.
 template <int S>
-__device__ void process_transform(CoeffShared& sh, int warp, int ox, int oy, int bx, int by, const CoeffArgs& A, int kind,
-                                  int order_class, int lane) {
+__device__ void process_transform(CoeffShared& sh, int warp, bool active, int ox, int oy, int bx, int by, const CoeffArgs& A,
+                                  int kind, int order_class, int lane) {
   constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int W = R > C ? R : C, H = R > C ? C : R, xs = W / 8, ys = H / 8, cxb = C / 8, cyb = R / 8, n = cxb * cyb, size = R * C;
+  constexpr int W = R > C ? R : C, H = R > C ? C : R, cxb = C / 8, cyb = R / 8, n = cxb * cyb, size = R * C;
+  constexpr int GS = W;                                    // lanes per transform
   const FrameDim& fd = A.fd;
-  const int gl = lane;
-  float* bc[3] = {sh.buf[warp][0], sh.buf[warp][1], sh.buf[warp][2]};
-  float* bt = sh.buf[warp][3];
+  const int gl = lane & (GS - 1), gbase = lane & ~(GS - 1), go = (lane / GS) * GS * kTPitch;
+  // (every templated helper below has ONE call site inside a non-unrolled channel loop: the kernel holds ten
+  // strategy instantiations and instruction-cache misses were 29 % of its stalls when each helper was inlined 3x)
+  float* bufs[3] = {sh.buf[warp][0] + go, sh.buf[warp][1] + go, sh.buf[warp][2] + go};
   const int po = oy * kTPitch + ox;
 #pragma unroll 1
-  for (int c = 0; c < 3; ++c) fwd_transform<S>(sh.px[c] + po, kTPitch, bt, bc[c], gl);
+  for (int c = 0; c < 3; ++c) fwd_transform<S>(sh.px[c] + po, kTPitch, bufs[c], bufs[c], gl);
+  float* b0 = bufs[0]; float* b1 = bufs[1]; float* b2 = bufs[2];
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   const size_t bi = (size_t)by * fd.bxs + bx;
   const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
   // ---- DC of every covered block (AddVarDCTDC quantisation: Y first, B with the 1.0 base correlation)
-  if (lane == 0) {
+  if (gl == 0 && active) {
     float dc[3][16];
 #pragma unroll 1
-    for (int c = 0; c < 3; ++c) dc_from_llf<S>(bc[c], dc[c]);
+    for (int c = 0; c < 3; ++c) dc_from_llf<S>(bufs[c], dc[c]);
     const int quant_dc = A.qd->quant_dc;
     const float gsq = scale * (float)quant_dc;
     const float inv_quant_dc = inv_gs / (float)quant_dc;
@@ -262,56 +270,50 @@ __device__ void process_transform(CoeffShared& sh, int warp, int ox, int oy, int
       A.dc_quant[2 * nblk + bj] = (int16_t)(ib > 32767 ? 32767 : (ib < -32768 ? -32768 : ib));
     }
   }
-  // ---- quant adjust
+  // ---- quant adjust (channel order Y, X, B; the result is the maximum, Y's thresholds are kept)
   const float* qm = A.T.w[kind];
   const float* dq = A.T.dq[kind];
-  int quant = A.raw_qf[bi];
+  int quant = active ? A.raw_qf[bi] : 1;
   float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
   if (A.adjust) {
     const int orig = quant;
     int maxq = 0;
-    {
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+      const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
       float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      maxq = adjust_quant<S>(bc[1], qm + size, 1, scale, 1.0f, orig, thr, gl);
-      thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3];
+      const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+      maxq = max(maxq, adjust_quant<S>(bufs[c], qm + c * size, c, scale, mulc, orig, thr, gl));
+      if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
     }
-    {
-      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      maxq = max(maxq, adjust_quant<S>(bc[0], qm, 0, scale, A.x_qm_mul, orig, thr, gl));
-    }
-    {
-      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      maxq = max(maxq, adjust_quant<S>(bc[2], qm + 2 * size, 2, scale, A.b_qm_mul, orig, thr, gl));
-    }
-    quant = __shfl_sync(0xffffffffu, maxq, 0);
-    thr_y[0] = __shfl_sync(0xffffffffu, thr_y[0], 0); thr_y[1] = __shfl_sync(0xffffffffu, thr_y[1], 0);
-    thr_y[2] = __shfl_sync(0xffffffffu, thr_y[2], 0); thr_y[3] = __shfl_sync(0xffffffffu, thr_y[3], 0);
+    quant = __shfl_sync(0xffffffffu, maxq, gbase);
+    thr_y[0] = __shfl_sync(0xffffffffu, thr_y[0], gbase); thr_y[1] = __shfl_sync(0xffffffffu, thr_y[1], gbase);
+    thr_y[2] = __shfl_sync(0xffffffffu, thr_y[2], gbase); thr_y[3] = __shfl_sync(0xffffffffu, thr_y[3], gbase);
   } else {
     thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f;
   }
-  // ---- quantise Y, roundtrip, remove chroma-from-luma, quantise X and B (all row-local)
+  // ---- quantise Y in place, roundtrip, remove chroma-from-luma, quantise X and B in place (all row-local)
   const float qac = scale * (float)quant;
-  int* qy = reinterpret_cast<int*>(bt);
-  quantize_rows<S>(bc[1], qm + size, 1, qac * 1.0f, thr_y, qy, gl);
+  const int* qy = reinterpret_cast<const int*>(b1);
   const float inv_qac = inv_gs / (float)quant;
   const int tx = bx >> 3, ty = by >> 3;
   const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
   const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
-  if (gl < H) {
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+    if (it == 1 && gl < H) {
 #pragma unroll 8
-    for (int x = 0; x < W; ++x) {
-      const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dq[size + gl * W + x]) * inv_qac;
-      bc[0][gl * kTPitch + x] = __fmaf_rn(-x_factor, yrt, bc[0][gl * kTPitch + x]);
-      bc[2][gl * kTPitch + x] = __fmaf_rn(-b_factor, yrt, bc[2][gl * kTPitch + x]);
+      for (int x = 0; x < W; ++x) {
+        const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dq[size + gl * W + x]) * inv_qac;
+        b0[gl * kTPitch + x] = __fmaf_rn(-x_factor, yrt, b0[gl * kTPitch + x]);
+        b2[gl * kTPitch + x] = __fmaf_rn(-b_factor, yrt, b2[gl * kTPitch + x]);
+      }
     }
-  }
-  {
     float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-    quantize_rows<S>(bc[0], qm, 0, qac * A.x_qm_mul, thr, reinterpret_cast<int*>(bc[0]), gl);
-  }
-  {
-    float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-    quantize_rows<S>(bc[2], qm + 2 * size, 2, qac * A.b_qm_mul, thr, reinterpret_cast<int*>(bc[2]), gl);
+    if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
+    const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+    quantize_rows<S>(bufs[c], qm + c * size, c, qac * mulc, thr, reinterpret_cast<int*>(bufs[c]), gl);
   }
   // ---- scan-order output + non-zero statistics
   const uint16_t* inv = A.inv_order[order_class];
@@ -319,9 +321,9 @@ __device__ void process_transform(CoeffShared& sh, int warp, int ox, int oy, int
 #pragma unroll 1
   for (int slot = 0; slot < 3; ++slot) {
     const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
-    const int* src = c == 1 ? qy : reinterpret_cast<const int*>(bc[c]);
+    const int* src = reinterpret_cast<const int*>(bufs[c]);
     int nz = 0, last = 0;
-    if (gl < H) {
+    if (gl < H && active) {
       for (int x = 0; x < W; ++x) {
         const int v = src[gl * kTPitch + x];
         const int k = inv[gl * W + x];
@@ -336,15 +338,31 @@ __device__ void process_transform(CoeffShared& sh, int warp, int ox, int oy, int
     nz = group_isum<H>(nz);
 #pragma unroll
     for (int st = H / 2; st >= 1; st >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, st));
-    if (lane == 0) {
+    if (gl == 0 && active) {
       const int shared = (nz + n - 1) >> log2n;
       A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nz;
       A.lastk[(size_t)c * nblk + bi] = (uint16_t)last;
       for (int j = 0; j < n; ++j) A.nzeros[(size_t)c * nblk + bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = (uint8_t)shared;
     }
   }
-  if (lane == 0) for (int j = 0; j < n; ++j) A.raw_qf[bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = quant;
+  if (gl == 0 && active) for (int j = 0; j < n; ++j) A.raw_qf[bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = quant;
   __syncwarp();
+}
+
+// all transforms of strategy S whose first block lies in the square: `mask` has one bit per block of the square
+template <int S>
+__device__ void process_strategy(CoeffShared& sh, int warp, unsigned mask, int sbx, int sby, const CoeffArgs& A, int kind,
+                                 int order_class, int lane) {
+  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
+  constexpr int GS = R > C ? R : C, GPW = 32 / GS;
+  const int m = __popc(mask);
+  for (int base = warp * GPW; base < m; base += kCoeffWarps * GPW) {
+    const int idx = base + lane / GS;
+    const bool active = idx < m;
+    const int b = active ? (int)__fns(mask, 0, idx + 1) : 0;
+    const int lx = b & 3, ly = b >> 2;
+    process_transform<S>(sh, warp, active, lx * 8, ly * 8, sbx + lx, sby + ly, A, kind, order_class, lane);
+  }
 }
 
 __global__ void __launch_bounds__(kCoeffWarps * 32) k_coeff_general(const float* __restrict__ X, const float* __restrict__ Y,
@@ -364,29 +382,29 @@ __global__ void __launch_bounds__(kCoeffWarps * 32) k_coeff_general(const float*
     sh.px[1][y * kTPitch + x] = in ? Y[g] : 0.0f;
     sh.px[2][y * kTPitch + x] = in ? B[g] : 0.0f;
   }
-  __syncthreads();
-  int seen = 0;
-  for (int b = 0; b < 16; ++b) {
-    const int lx = b & 3, ly = b >> 2;
-    if (lx >= bw || ly >= bh) continue;
-    const uint8_t a = acs[(size_t)(sby + ly) * fd.bxs + sbx + lx];
-    if (!(a & 0x80)) continue;
-    if ((seen++ % kCoeffWarps) != warp) continue;
-    const int s = a & 0x7f, ox = lx * 8, oy = ly * 8, bx = sbx + lx, by = sby + ly;
-    switch (s) {
-      case kStratDCT: process_transform<kStratDCT>(sh, warp, ox, oy, bx, by, A, 0, 0, lane); break;
-      case kStratDCT4X4: process_transform<kStratDCT4X4>(sh, warp, ox, oy, bx, by, A, 3, 1, lane); break;
-      case kStratDCT4X8: process_transform<kStratDCT4X8>(sh, warp, ox, oy, bx, by, A, 9, 1, lane); break;
-      case kStratDCT8X4: process_transform<kStratDCT8X4>(sh, warp, ox, oy, bx, by, A, 9, 1, lane); break;
-      case kStratDCT16X16: process_transform<kStratDCT16X16>(sh, warp, ox, oy, bx, by, A, 4, 2, lane); break;
-      case kStratDCT32X32: process_transform<kStratDCT32X32>(sh, warp, ox, oy, bx, by, A, 5, 3, lane); break;
-      case kStratDCT16X8: process_transform<kStratDCT16X8>(sh, warp, ox, oy, bx, by, A, 6, 4, lane); break;
-      case kStratDCT8X16: process_transform<kStratDCT8X16>(sh, warp, ox, oy, bx, by, A, 6, 4, lane); break;
-      case kStratDCT32X16: process_transform<kStratDCT32X16>(sh, warp, ox, oy, bx, by, A, 8, 6, lane); break;
-      case kStratDCT16X32: process_transform<kStratDCT16X32>(sh, warp, ox, oy, bx, by, A, 8, 6, lane); break;
-      default: break;
+  // strategy of the square's blocks: lane b < 16 looks at block b; one ballot per strategy gives its transform list
+  int my_s = -1;
+  if (lane < 16) {
+    const int lx = lane & 3, ly = lane >> 2;
+    if (lx < bw && ly < bh) {
+      const uint8_t a = acs[(size_t)(sby + ly) * fd.bxs + sbx + lx];
+      if (a & 0x80) my_s = a & 0x7f;
     }
   }
+  __syncthreads();
+#define JXLB_STRATEGY(S, KIND, ORD) \
+  { const unsigned mk = __ballot_sync(0xffffffffu, my_s == S); if (mk) process_strategy<S>(sh, warp, mk, sbx, sby, A, KIND, ORD, lane); }
+  JXLB_STRATEGY(kStratDCT, 0, 0)
+  JXLB_STRATEGY(kStratDCT4X4, 3, 1)
+  JXLB_STRATEGY(kStratDCT4X8, 9, 1)
+  JXLB_STRATEGY(kStratDCT8X4, 9, 1)
+  JXLB_STRATEGY(kStratDCT16X8, 6, 4)
+  JXLB_STRATEGY(kStratDCT8X16, 6, 4)
+  JXLB_STRATEGY(kStratDCT16X16, 4, 2)
+  JXLB_STRATEGY(kStratDCT32X16, 8, 6)
+  JXLB_STRATEGY(kStratDCT16X32, 8, 6)
+  JXLB_STRATEGY(kStratDCT32X32, 5, 3)
+#undef JXLB_STRATEGY
 }
 
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,

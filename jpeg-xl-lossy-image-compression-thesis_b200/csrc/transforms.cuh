@@ -70,8 +70,9 @@ template <int N> __device__ __forceinline__ void idct1d(float* v) {
 }
 
 // ---- plain R x C DCT (strategies DCT, DCT16X16, DCT32X32, DCTrXc rectangles) --------------------
-// px: pixel tile in shared memory (row pitch px_pitch), t: scratch, out: coefficient block, both
-// [.][kTPitch].  gl = lane within the group.  All lanes of the warp must call (contains __syncwarp).
+// px: pixel tile in shared memory (row pitch px_pitch); t / out: [.][kTPitch] buffers that MAY BE THE SAME
+// buffer (every stage reads all of its inputs into registers, synchronises, then writes), so a transform
+// needs one scratch buffer only.  gl = lane within the group.  All lanes of the warp must call.
 template <int R, int C>
 __device__ __forceinline__ void fwd_dct2d(const float* px, int px_pitch, float* t, float* out, int gl) {
   if (gl < R) {
@@ -83,17 +84,22 @@ __device__ __forceinline__ void fwd_dct2d(const float* px, int px_pitch, float* 
     for (int x = 0; x < C; ++x) t[gl * kTPitch + x] = v[x];      // t[r][hf]
   }
   __syncwarp();
-  if (gl < C) {
+  {
     float v[R];
+    if (gl < C) {
 #pragma unroll
-    for (int y = 0; y < R; ++y) v[y] = t[y * kTPitch + gl];
-    dct1d<R>(v);
-    if constexpr (R >= C) {
+      for (int y = 0; y < R; ++y) v[y] = t[y * kTPitch + gl];
+    }
+    __syncwarp();   // t and out may alias
+    if (gl < C) {
+      dct1d<R>(v);
+      if constexpr (R >= C) {
 #pragma unroll
-      for (int y = 0; y < R; ++y) out[gl * kTPitch + y] = v[y];  // out[hf][vf]: coefficient row = hf
-    } else {
+        for (int y = 0; y < R; ++y) out[gl * kTPitch + y] = v[y];  // out[hf][vf]: coefficient row = hf
+      } else {
 #pragma unroll
-      for (int y = 0; y < R; ++y) out[y * kTPitch + gl] = v[y];  // out[vf][hf]: coefficient row = vf
+        for (int y = 0; y < R; ++y) out[y * kTPitch + gl] = v[y];  // out[vf][hf]: coefficient row = vf
+      }
     }
   }
   __syncwarp();
@@ -102,18 +108,23 @@ __device__ __forceinline__ void fwd_dct2d(const float* px, int px_pitch, float* 
 // coef: coefficient block [H][kTPitch]; t: scratch; px: output pixel tile [R][kTPitch]
 template <int R, int C>
 __device__ __forceinline__ void inv_dct2d(const float* coef, float* t, float* px, int gl) {
-  if (gl < C) {
+  {
     float v[R];
-    if constexpr (R >= C) {
+    if (gl < C) {
+      if constexpr (R >= C) {
 #pragma unroll
-      for (int y = 0; y < R; ++y) v[y] = coef[gl * kTPitch + y];
-    } else {
+        for (int y = 0; y < R; ++y) v[y] = coef[gl * kTPitch + y];
+      } else {
 #pragma unroll
-      for (int y = 0; y < R; ++y) v[y] = coef[y * kTPitch + gl];
+        for (int y = 0; y < R; ++y) v[y] = coef[y * kTPitch + gl];
+      }
     }
-    idct1d<R>(v);
+    __syncwarp();   // coef and t may alias
+    if (gl < C) {
+      idct1d<R>(v);
 #pragma unroll
-    for (int y = 0; y < R; ++y) t[y * kTPitch + gl] = v[y];      // t[y][hf]
+      for (int y = 0; y < R; ++y) t[y * kTPitch + gl] = v[y];      // t[y][hf]
+    }
   }
   __syncwarp();
   if (gl < R) {
@@ -131,10 +142,13 @@ __device__ __forceinline__ void inv_dct2d(const float* coef, float* t, float* px
 enum { kStratDCT = 0, kStratDCT4X4 = 3, kStratDCT16X16 = 4, kStratDCT32X32 = 5, kStratDCT16X8 = 6, kStratDCT8X16 = 7,
        kStratDCT32X16 = 10, kStratDCT16X32 = 11, kStratDCT4X8 = 12, kStratDCT8X4 = 13 };
 
+// All of them are alias-safe like the plain transform (t / out / px may be one buffer): every stage loads
+// into registers, synchronises, then stores.
+
 // DCT4X4: four 4x4 DCTs interleaved, then the 2x2 Hadamard of their DCs (oracle TransformFromPixels)
 __device__ __forceinline__ void fwd_dct4x4(const float* px, int px_pitch, float* t, float* out, int gl) {
+  float a[4], b[4];
   if (gl < 8) {
-    float a[4], b[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) { a[x] = px[gl * px_pitch + x]; b[x] = px[gl * px_pitch + 4 + x]; }
     dct1d<4>(a); dct1d<4>(b);
@@ -143,10 +157,12 @@ __device__ __forceinline__ void fwd_dct4x4(const float* px, int px_pitch, float*
   }
   __syncwarp();
   if (gl < 8) {
-    const int x = gl >> 2, hf = gl & 3;     // column gl = quadrant column x, horizontal frequency hf
-    float a[4], b[4];
 #pragma unroll
     for (int y = 0; y < 4; ++y) { a[y] = t[y * kTPitch + gl]; b[y] = t[(4 + y) * kTPitch + gl]; }
+  }
+  __syncwarp();
+  if (gl < 8) {
+    const int x = gl >> 2, hf = gl & 3;     // column gl = quadrant column x, horizontal frequency hf
     dct1d<4>(a); dct1d<4>(b);
     // d[hf*4 + vf] of quadrant (y, x) -> coef[(y + hf*2)*8 + x + vf*2]
 #pragma unroll
@@ -176,18 +192,20 @@ __device__ __forceinline__ void inv_dct4x4(float* coef, float* t, float* px, int
     coef[kTPitch + 1] = b00 - b01 - b10 + b11;
   }
   __syncwarp();
+  float a[4], b[4];
   if (gl < 8) {
     const int x = gl >> 2, hf = gl & 3;
-    float a[4], b[4];
 #pragma unroll
     for (int vf = 0; vf < 4; ++vf) { a[vf] = coef[(0 + hf * 2) * kTPitch + x + vf * 2]; b[vf] = coef[(1 + hf * 2) * kTPitch + x + vf * 2]; }
+  }
+  __syncwarp();
+  if (gl < 8) {
     idct1d<4>(a); idct1d<4>(b);
 #pragma unroll
     for (int y = 0; y < 4; ++y) { t[y * kTPitch + gl] = a[y]; t[(4 + y) * kTPitch + gl] = b[y]; }
   }
   __syncwarp();
   if (gl < 8) {
-    float a[4], b[4];
 #pragma unroll
     for (int x = 0; x < 4; ++x) { a[x] = t[gl * kTPitch + x]; b[x] = t[gl * kTPitch + 4 + x]; }
     idct1d<4>(a); idct1d<4>(b);
@@ -208,11 +226,14 @@ __device__ __forceinline__ void fwd_dct4x8(const float* px, int px_pitch, float*
     for (int x = 0; x < 4; ++x) { t[gl * kTPitch + x] = a[x]; t[gl * kTPitch + 4 + x] = b[x]; }
   }
   __syncwarp();
+  float v[8];
   if (gl < 8) {
-    const int x = gl >> 2, hf = gl & 3;
-    float v[8];
 #pragma unroll
     for (int y = 0; y < 8; ++y) v[y] = t[y * kTPitch + gl];
+  }
+  __syncwarp();
+  if (gl < 8) {
+    const int x = gl >> 2, hf = gl & 3;
     dct1d<8>(v);
 #pragma unroll
     for (int vf = 0; vf < 8; ++vf) out[(x + hf * 2) * kTPitch + vf] = v[vf];
@@ -232,11 +253,14 @@ __device__ __forceinline__ void inv_dct4x8(float* coef, float* t, float* px, int
     coef[0] = b0 + b1; coef[kTPitch] = b0 - b1;
   }
   __syncwarp();
+  float v[8];
   if (gl < 8) {
     const int x = gl >> 2, hf = gl & 3;
-    float v[8];
 #pragma unroll
     for (int vf = 0; vf < 8; ++vf) v[vf] = coef[(x + hf * 2) * kTPitch + vf];
+  }
+  __syncwarp();
+  if (gl < 8) {
     idct1d<8>(v);
 #pragma unroll
     for (int y = 0; y < 8; ++y) t[y * kTPitch + gl] = v[y];
@@ -264,10 +288,13 @@ __device__ __forceinline__ void fwd_dct8x4(const float* px, int px_pitch, float*
     for (int x = 0; x < 8; ++x) t[gl * kTPitch + x] = v[x];
   }
   __syncwarp();
+  float a[4], b[4];
   if (gl < 8) {
-    float a[4], b[4];
 #pragma unroll
     for (int y = 0; y < 4; ++y) { a[y] = t[y * kTPitch + gl]; b[y] = t[(4 + y) * kTPitch + gl]; }
+  }
+  __syncwarp();
+  if (gl < 8) {
     dct1d<4>(a); dct1d<4>(b);
 #pragma unroll
     for (int vf = 0; vf < 4; ++vf) { out[(0 + vf * 2) * kTPitch + gl] = a[vf]; out[(1 + vf * 2) * kTPitch + gl] = b[vf]; }
@@ -287,10 +314,13 @@ __device__ __forceinline__ void inv_dct8x4(float* coef, float* t, float* px, int
     coef[0] = b0 + b1; coef[kTPitch] = b0 - b1;
   }
   __syncwarp();
+  float a[4], b[4];
   if (gl < 8) {
-    float a[4], b[4];
 #pragma unroll
     for (int vf = 0; vf < 4; ++vf) { a[vf] = coef[(0 + vf * 2) * kTPitch + gl]; b[vf] = coef[(1 + vf * 2) * kTPitch + gl]; }
+  }
+  __syncwarp();
+  if (gl < 8) {
     idct1d<4>(a); idct1d<4>(b);
 #pragma unroll
     for (int y = 0; y < 4; ++y) { t[y * kTPitch + gl] = a[y]; t[(4 + y) * kTPitch + gl] = b[y]; }

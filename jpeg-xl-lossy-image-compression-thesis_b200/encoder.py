@@ -80,7 +80,8 @@ class Stats:
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libjxlb200.so")
+    """In-tree libjxlb200.so ($JXLB200_LIB overrides it, e.g. to compare kernel variants)."""
+    return os.environ.get("JXLB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libjxlb200.so")
 
 
 _LIB = None

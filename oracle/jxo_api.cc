@@ -27,6 +27,8 @@ void* jxo_decode(const uint8_t* data, size_t size) {
   DecodeCodestream(data, size, f);
   return f;
 }
+// reconstructs h*w*3 sRGB bytes from a decoded frame (jxo_decode); returns 1 on success
+int jxo_reconstruct(void* h, uint8_t* rgb) { return ReconstructRgb(*(Frame*)h, rgb) ? 1 : 0; }
 const char* jxo_error(void* h) { return ((Frame*)h)->error.c_str(); }
 void jxo_free(void* h) { delete (Frame*)h; }
 

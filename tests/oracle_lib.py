@@ -38,6 +38,8 @@ class Oracle:
         lib.jxo_encode.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(Params)]
         lib.jxo_decode.restype = vp
         lib.jxo_decode.argtypes = [vp, ctypes.c_size_t]
+        lib.jxo_reconstruct.restype = ctypes.c_int
+        lib.jxo_reconstruct.argtypes = [vp, vp]
         lib.jxo_error.restype = ctypes.c_char_p
         lib.jxo_error.argtypes = [vp]
         lib.jxo_free.argtypes = [vp]
@@ -75,6 +77,15 @@ class Oracle:
         """self-decoder: codestream bytes -> Frame holding dc_quant / acs / raw_qf / coeffs / nzeros"""
         buf = np.frombuffer(bytes(codestream), dtype=np.uint8)
         return Frame(self, self.lib.jxo_decode(buf.ctypes.data, buf.size))
+
+    def decode_pixels(self, codestream, w, h):
+        """self-decoder to pixels: returns (h, w, 3) uint8 sRGB, or None when the stream is rejected"""
+        fr = self.decode(codestream)
+        if fr.error:
+            return None
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        ok = self.lib.jxo_reconstruct(fr.h, out.ctypes.data)
+        return out if ok else None
 
     def dims(self, w, h):
         d = (ctypes.c_int32 * 16)()

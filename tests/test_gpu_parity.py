@@ -237,3 +237,18 @@ def test_codestream_pins_gpu(pkg, encoder):
         data, _ = encoder.encode(pkg.synth_image(p["w"], p["h"], p["index"]), p["distance"], p["effort"], p["proposal"], p["flags"])
         assert len(data) == p["bytes"] and hashlib.sha256(data).hexdigest() == p["sha256"], p
         assert hashlib.sha256(encoder.dump("acs").tobytes()).hexdigest() == p["acs_sha256"], p
+
+
+def test_gpu_codestream_decodes_to_the_image(pkg, oracle, encoder):
+    """The CUDA path's codestream, decoded to pixels by the independent self-decoder, is the input image at the
+    quality the distance asks for (all strategies + the combined proposal)."""
+    img = pkg.synth_image(512, 384, 21)
+    prev = 99.0
+    for d, floor in ((0.5, 42.0), (1.0, 38.0), (3.0, 33.0)):
+        data, st = encoder.encode(img, d, 7, pkg.PROPOSAL_COMBINED, 0)
+        rec = oracle.decode_pixels(data, 512, 384)
+        assert rec is not None
+        mse = np.mean((img.astype(np.float64) - rec.astype(np.float64)) ** 2)
+        p = 10.0 * np.log10(255.0 ** 2 / mse)
+        assert floor < p < prev, (d, p)
+        prev = p

@@ -116,3 +116,36 @@ def test_partition_override_keeps_estimate(pkg, oracle):
     # every strategy the partitioning proposal introduces is one of its three outputs or a merge consequence
     assert changed.size > 0
     assert set(np.unique(acs1[changed] & 0x7F)) <= {0, 3, 12, 13, 4, 5, 6, 7, 10, 11}
+
+
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+
+
+def test_decoded_pixels_quality(pkg, oracle):
+    """Tier T2b: the self-decoder's pixel reconstruction (dequantise, DC -> LLF, chroma-from-luma, inverse
+    transforms of every emitted size, XYB -> sRGB) returns the input image at a quality that matches the
+    distance: PSNR falls monotonically with distance while bpp falls too, for both strategy modes."""
+    img = pkg.synth_image(384, 256, 21)
+    for flags in (1, 0):
+        last_psnr, last_size = 99.0, 1 << 30
+        for d, floor in ((0.5, 42.0), (1.0, 38.0), (2.0, 35.0), (4.0, 32.0), (8.0, 29.0)):
+            cs = oracle.encode(img, d, 7, 0, flags).dump("codestream")
+            rec = oracle.decode_pixels(cs.tobytes(), 384, 256)
+            assert rec is not None
+            p = _psnr(img, rec)
+            assert p > floor, (d, flags, p)
+            assert p < last_psnr and cs.size < last_size
+            last_psnr, last_size = p, cs.size
+
+
+def test_decoded_pixels_proposals_and_edges(pkg, oracle):
+    img = pkg.synth_image(200, 136, 5)                       # ragged size: padding must not leak into the picture
+    for proposal in (0, 1, 2, 3):
+        cs = oracle.encode(img, 1.0, 7, proposal, 0).dump("codestream")
+        rec = oracle.decode_pixels(cs.tobytes(), 200, 136)
+        assert rec is not None and _psnr(img, rec) > 37.0
+    flat = np.full((40, 72, 3), 200, dtype=np.uint8)
+    rec = oracle.decode_pixels(oracle.encode(flat, 1.0, 7, 3, 0).dump("codestream").tobytes(), 72, 40)
+    assert np.abs(rec.astype(int) - 200).max() <= 1

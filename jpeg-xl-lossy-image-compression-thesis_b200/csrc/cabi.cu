@@ -23,6 +23,7 @@ struct jxlb200_ctx {
   std::vector<Encoder*> extra;        // pipelines 1..P-1, created on first batch use
   int device = 0;
   int num_pipelines = 4;
+  int ans_gpw = 3;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::string err;
   Encoder* pipe(int i) { return i == 0 ? &enc : extra[i - 1]; }
 };
@@ -48,7 +49,7 @@ int jxlb200_abi_version(void) { return JXLB200_ABI_VERSION; }
 
 jxlb200_ctx* jxlb200_create(int device) {
   // one hardware work queue per pipeline stream; only effective when the CUDA context does not exist yet
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // (32 is the maximum the driver accepts)
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;
   cudaDeviceProp prop;
@@ -56,7 +57,8 @@ jxlb200_ctx* jxlb200_create(int device) {
   if (prop.major != 10) return nullptr;  // sm_100a only; there is no fallback path
   jxlb200_ctx* ctx = new jxlb200_ctx();
   ctx->device = device;
-  if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 32) ctx->num_pipelines = v; }
+  if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->num_pipelines = v; }
+  if (const char* env = getenv("JXLB200_ANS_GPW")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->ans_gpw = v; }
   std::string e;
   if (!ctx->enc.Init(device, &e)) { delete ctx; return nullptr; }
   return ctx;
@@ -144,7 +146,7 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
     retire(p);
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
-    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? 3 : 1);
+    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
     if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
       rc = fail(ctx, e);
       break;
@@ -191,7 +193,7 @@ int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels
     retire(p);
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
-    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? 3 : 1);
+    ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
     const auto tq0 = std::chrono::steady_clock::now();
     if (!ctx->pipe(p)->EnqueueDevice(d_pixels[i], (int)widths[i], (int)heights[i], strides[i], ep, &e)) { rc = fail(ctx, e); break; }
     enqueue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();
@@ -218,7 +220,7 @@ int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels
 
 int jxlb200_set_pipelines(jxlb200_ctx* ctx, int n) {
   if (!ctx) return -1;
-  if (n < 1 || n > 32) return fail(ctx, "pipelines out of range [1, 32]");
+  if (n < 1 || n > 64) return fail(ctx, "pipelines out of range [1, 64]");
   ctx->num_pipelines = n;
   return 0;
 }

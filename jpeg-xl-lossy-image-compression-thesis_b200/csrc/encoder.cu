@@ -42,6 +42,16 @@ bool Encoder::Init(int device, std::string* err) {
     CUDA_OK(cudaMemcpy(d_dequant_[k].p, dq.data(), dq.size() * 4, cudaMemcpyHostToDevice));
   }
   {
+    std::vector<float> w8, dq8;
+    host_quant_weights(0, &w8);
+    dq8.resize(64);
+    for (int i = 0; i < 64; ++i) dq8[i] = 1.0f / w8[64 + i];
+    if (!dct8_v2_upload_tables(w8.data(), dq8.data())) { *err = "constant upload"; return false; }
+    // default: 8 lanes per block (k_dct_quant.cu, 0.102 ms per 4K frame); the thread-per-block design
+    // (k_dct8_v2.cu) measured 0.120 ms and is kept as an opt-in for comparison
+    dct8_v1_ = getenv("JXLB200_DCT8_V2") == nullptr;
+  }
+  {
     std::vector<uint16_t> order;
     host_natural_order(0, &order);
     uint8_t izz[64];
@@ -275,9 +285,13 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
                          p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
                          stream_);
   } else {
-    launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
-                      b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
-                      d_nzcount_.p, d_lastk_.p, stream_);
+    if (dct8_v1_)
+      launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
+                        b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
+                        d_nzcount_.p, d_lastk_.p, stream_);
+    else
+      launch_dct8_quant_v2(X, Y, B, fd, d_q_.p, d_cmap_.p, x_qm_mul_, b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p,
+                           d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
   // K8: tokens + per-context histograms

@@ -48,6 +48,7 @@ class Encoder {
   bool Reserve(const FrameDim& fd, std::string* err);
   bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
   bool in_flight_ = false;
+  bool dct8_v1_ = false;
   int ans_groups_per_warp_ = 1;
   unsigned launches_ = 0;
 

@@ -7,7 +7,7 @@ imgs = [pkg.synth_image(w, h, i) for i in range(8)]
 d = [torch.from_numpy(im).cuda() for im in imgs]
 names = ["h2d","xyb","aq","homog","acs","coeff","tok","histo","ans","dc","asm"]
 enc = pkg.Encoder(0)
-for P, B in ((1, 8), (4, 8), (8, 8), (8, 16), (8, 32), (16, 32)):
+for P, B in ((32, 64), (48, 96), (64, 128)):
     enc.set_pipelines(P)
     ptrs = [d[i % 8].data_ptr() for i in range(B)]
     for _ in range(2):
@@ -16,5 +16,5 @@ for P, B in ((1, 8), (4, 8), (8, 8), (8, 16), (8, 32), (16, 32)):
     sts, ms = enc.encode_batch_device(ptrs, w, h, 3 * w, 1.0, 7, 0, 1)
     wall = (time.perf_counter() - t0) * 1e3
     sm = np.mean([s.stage_ms[:11] for s in sts], axis=0)
-    print(f"P={P} B={B} dev_ms={ms:.2f} wall={wall:.2f} per_img={ms/B:.2f} total_per_img={np.mean([s.total_ms for s in sts]):.2f}")
+    print(f"P={P} B={B} dev_ms={ms:.2f} wall={wall:.2f} per_img={ms/B:.3f} GP/s={B*w*h/1e6/ms:.2f} latency_per_img={np.mean([s.total_ms for s in sts]):.2f}")
     print("   ", {n: round(float(v), 2) for n, v in zip(names, sm)})

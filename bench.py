@@ -177,8 +177,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=32, help="images per rank per step")
-    ap.add_argument("--pipelines", type=int, default=16, help="images in flight per rank (CUDA streams)")
+    ap.add_argument("--batch", type=int, default=64, help="images per rank per step")
+    ap.add_argument("--pipelines", type=int, default=32, help="images in flight per rank (CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,11 +201,12 @@ def main():
     w, h, distance, effort, proposal, flags = WORKLOADS[args.workload]
     mp = w * h / 1e6
     B = args.batch                               # images per rank per step, args.pipelines of them in flight
-    imgs = [pkg.synth_image(w, h, rank * 64 + i) for i in range(B)]
+    n_distinct = min(B, 8)                       # distinct synthetic images per rank (the batch cycles through them)
+    imgs = [pkg.synth_image(w, h, rank * 64 + i) for i in range(n_distinct)]
     pinned = [torch.from_numpy(im).pin_memory() for im in imgs]          # e2e inputs: page-locked host memory
-    h_imgs = [p.numpy() for p in pinned]
+    h_imgs = [pinned[i % n_distinct].numpy() for i in range(B)]
     d_imgs = [p.cuda() for p in pinned]                                  # value inputs: resident in HBM
-    d_ptrs = [d.data_ptr() for d in d_imgs]
+    d_ptrs = [d_imgs[i % n_distinct].data_ptr() for i in range(B)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     enc = pkg.Encoder(local_rank)
@@ -242,7 +243,7 @@ def main():
     for i in range(max(3, min(args.steps, 10))):
         flush.fill_(i & 255)
         torch.cuda.synchronize()
-        st1 = enc.encode_device(d_ptrs[i % B], w, h, 3 * w, distance, effort, proposal, flags)
+        st1 = enc.encode_device(d_ptrs[i % n_distinct], w, h, 3 * w, distance, effort, proposal, flags)
         stage_ms.append(list(st1.stage_ms) + [st1.total_ms])
 
     # ---- e2e: pinned host buffers through jxlb200_encode_batch, wall clock around the calls ----
@@ -294,8 +295,8 @@ def main():
             "config": {"workload": args.workload, "width": w, "height": h, "distance": distance, "effort": effort,
                        "proposal": proposal, "flags": flags, "images_per_rank_per_step": B,
                        "pipelines_per_rank": args.pipelines,
-                       "l2": "flushed between timed iterations (256 MiB fill, untimed); inputs per step "
-                             f"{B * 3 * w * h >> 20} MiB",
+                       "l2": "flushed between timed iterations (256 MiB fill, untimed); distinct inputs per step "
+                             f"{n_distinct * 3 * w * h >> 20} MiB",
                        "parallelism": f"image-sharded x{world}, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * 3 * w * h,

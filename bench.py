@@ -43,7 +43,7 @@ WORKLOADS = {
 STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
 # DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), per workload kernel;
 # filled from profiles/ (None = not captured for this kernel)
-TRAFFIC_BYTES = {"coeff": 125.3e6}
+TRAFFIC_BYTES = {"coeff": 128.3e6}   # profiles/r01d_hbm_kernels_full.txt: 100.1 MB read + 28.2 MB written
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -308,9 +308,9 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             cores = 1
-            v, dt = cpu_oracle_throughput(args.workload, 2, 1)
+            v, dt = cpu_oracle_throughput(args.workload, 10, 1)
             line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
-                                    "sample": f"2 images of {w}x{h}, scalar oracle, 1 thread, {dt:.1f} s"}
+                                    "sample": f"10 images of {w}x{h}, scalar oracle, 1 thread, {dt:.1f} s"}
         print(json.dumps(line), flush=True)
     enc.close()
     if world > 1:

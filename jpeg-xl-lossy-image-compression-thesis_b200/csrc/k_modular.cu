@@ -41,27 +41,39 @@ __global__ void __launch_bounds__(1024) k_mod_ranks(const uint8_t* __restrict__ 
   const int total = d.w * d.h;
   if (t == 0) s_carry = 0;
   __syncthreads();
-  for (int i0 = 0; i0 < total; i0 += 1024) {
-    const int i = i0 + t;
-    uint8_t a = 0; size_t bi = 0;
-    if (i < total) {
-      const int y = i / d.w, x = i - y * d.w;
-      bi = (size_t)(d.y0 + y) * fd.bxs + d.x0 + x;
-      a = acs[bi];
+  // 4 consecutive raster positions per thread and iteration (their loads are issued together)
+  for (int i0 = 0; i0 < total; i0 += 4096) {
+    uint8_t a[4]; size_t bi[4];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + t * 4 + u;
+      a[u] = 0; bi[u] = 0;
+      if (i < total) {
+        const int y = i / d.w, x = i - y * d.w;
+        bi[u] = (size_t)(d.y0 + y) * fd.bxs + d.x0 + x;
+        a[u] = acs[bi[u]];
+      }
     }
-    const bool first = (a & 0x80) != 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, first);
-    if (lane == 0) s_warp[warp] = (uint32_t)__popc(bal);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cnt += (a[u] >> 7) & 1;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= dd) incl += o; }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t base = s_carry;
+    uint32_t base = s_carry + incl - cnt;
     for (int w = 0; w < warp; ++w) base += s_warp[w];
-    if (first) {
-      const uint32_t r = base + (uint32_t)__popc(bal & ((1u << lane) - 1));
-      strat_c[d.block_base + r] = a & 0x7f;
-      qf_c[d.block_base + r] = raw_qf[bi] - 1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (a[u] & 0x80) {
+        strat_c[d.block_base + base] = a[u] & 0x7f;
+        qf_c[d.block_base + base] = raw_qf[bi[u]] - 1;
+        ++base;
+      }
     }
     __syncthreads();
-    if (t == 1023) s_carry = base + (uint32_t)__popc(bal);
+    if (t == 1023) s_carry = base;
     __syncthreads();
   }
   if (t == 0) first_count[blockIdx.x] = s_carry;

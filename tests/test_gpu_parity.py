@@ -76,6 +76,9 @@ def test_error_behaviour(pkg, encoder):
             encoder.encode(img, **kwargs)
     with pytest.raises(pkg.EncodeError):
         encoder.encode(np.zeros((4, 4), dtype=np.uint8))
+    for shape in ((0, 0, 3), (0, 8, 3), (8, 0, 3)):          # empty inputs are refused, not crashed on
+        with pytest.raises(pkg.EncodeError):
+            encoder.encode(np.zeros(shape, dtype=np.uint8))
     encoder.encode(img)   # the context stays usable after an error (skip-and-continue)
 
 

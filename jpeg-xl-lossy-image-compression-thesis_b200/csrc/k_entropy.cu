@@ -126,14 +126,24 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
         if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
       }
     }
+    // coefficient tokens: a (block, channel) has ~4.5 of them on average, so four entries are walked side by side,
+    // eight lanes each (the running non-zero count comes from the group's byte of the ballot)
     unsigned todo = __ballot_sync(0xffffffffu, m_count > 1);
+    const int gi = lane >> 3, gl = lane & 7;
     while (todo) {
-      const int j = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t off = __shfl_sync(0xffffffffu, m_off, j);
-      const uint32_t count = __shfl_sync(0xffffffffu, m_count, j);
-      const uint32_t misc = __shfl_sync(0xffffffffu, m_misc, j);
-      const int ee = e0 + j;
+      int j = -1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jj = todo ? __ffs(todo) - 1 : -1;
+        if (todo) todo &= todo - 1;
+        if (q == gi) j = jj;
+      }
+      const bool active = j >= 0;
+      const int src = active ? j : 0;
+      const uint32_t off = __shfl_sync(0xffffffffu, m_off, src);
+      const uint32_t count = __shfl_sync(0xffffffffu, m_count, src);
+      const uint32_t misc = __shfl_sync(0xffffffffu, m_misc, src);
+      const int ee = e0 + src;
       const int blk = ee / 3, slot = ee - blk * 3;
       const int lx = blk & 31, ly = blk >> 5;
       const int s = misc & 0xff, block_ctx = (misc >> 8) & 0xff;
@@ -142,9 +152,9 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
       const int log2n = 31 - __clz(n);
       const int histo_offset = kNumBlockCtx * kNonZeroBuckets + kZeroDensityContextCount * block_ctx;
       int prev_carry = nz > size / 16 ? 0 : 1;
-      const int last = n + (int)count - 2;  // scan position of the last non-zero coefficient
-      for (int k0 = n; k0 <= last; k0 += 32) {
-        const int k = k0 + lane;
+      const int last = active ? n + (int)count - 2 : -1;  // scan position of the last non-zero coefficient
+      for (int k0 = n; __any_sync(0xffffffffu, k0 <= last); k0 += 8) {
+        const int k = k0 + gl;
         int coef = 0;
         if (k <= last) {
           const int jj = k >> 6;
@@ -152,9 +162,9 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
           const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
           coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
         }
-        const unsigned mask = __ballot_sync(0xffffffffu, coef != 0);
-        const int nz_here = nz - __popc(mask & ((1u << lane) - 1));
-        const int prev = lane == 0 ? prev_carry : (int)((mask >> (lane - 1)) & 1);
+        const unsigned mask = (__ballot_sync(0xffffffffu, coef != 0) >> (gi * 8)) & 0xFFu;
+        const int nz_here = nz - __popc(mask & ((1u << gl) - 1));
+        const int prev = gl == 0 ? prev_carry : (int)((mask >> (gl - 1)) & 1);
         if (k <= last) {
           const int nzl = (nz_here + n - 1) >> log2n;
           const uint32_t ctx = (uint32_t)(histo_offset + (c_nnz_ctx[nzl] + c_freq_ctx[k >> log2n]) * 2 + prev);
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
           if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
         }
         nz -= __popc(mask);
-        prev_carry = (int)(mask >> 31);
+        prev_carry = (int)(mask >> 7);
       }
     }
   }

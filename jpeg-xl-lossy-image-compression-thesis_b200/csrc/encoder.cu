@@ -73,10 +73,10 @@ bool Encoder::Init(int device, std::string* err) {
         d_rmap_.Reserve((size_t)kMaxClusters * kAnsTabSize) && d_mod_hist_.Reserve(kNumModularCtx * kModAlphabet) &&
         d_lf_words_.Reserve(4096) && d_small_.Reserve(16) && d_tree_words_.Reserve(256) &&
         d_code_len_.Reserve(kNumModularCtx * kModAlphabet) && d_code_bits_.Reserve(kNumModularCtx * kModAlphabet) &&
-        d_cm_back_.Reserve(8192) && d_hf_words_.Reserve(8192 + kMaxClusters * 64 + 256) && d_out_info_.Reserve(8))) {
+        d_cm_back_.Reserve(8192) && d_hf_words_.Reserve(8192 + kMaxClusters * 64 + 256) && d_out_info_.Reserve(40))) {
     *err = "alloc"; return false;
   }
-  CUDA_OK(cudaMallocHost(&h_out_info_, 8 * sizeof(unsigned long long)));
+  CUDA_OK(cudaMallocHost(&h_out_info_, 40 * sizeof(unsigned long long)));
   {
     // inverse natural coefficient orders of the order classes the search can emit
     static const int rep[13] = {0, 3, 4, 5, 6, 8, 10, -1, -1, -1, -1, -1, -1};
@@ -319,7 +319,9 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   }
   CUDA_OK(cudaMemsetAsync(d_mod_hist_.p, 0, kNumModularCtx * kModAlphabet * 4, stream_));
   CUDA_OK(cudaMemsetAsync(d_mod_words_.p, 0, ((size_t)total_elems_ + 2) * 4, stream_));
-  launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, stream_);
+  CUDA_OK(cudaMemsetAsync(d_out_info_.p + 8, 0, 32 * sizeof(unsigned long long), stream_));   // acs histogram slots
+  launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p,
+                   d_out_info_.p + 8, stream_);
   launch_mod_tokens(d_dc_quant_.p, d_cmap_.p, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, fd, d_dgs_.p, fd.num_dc_groups,
                     total_elems_, d_mod_tokens_.p, d_mod_hist_.p, stream_);
   launch_mod_codes(d_mod_hist_.p, d_q_.p, d_tree_words_.p, tree_bits, d_code_len_.p, d_code_bits_.p, d_lf_words_.p, lf_bits,
@@ -336,7 +338,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   launch_assemble(d_sections_.p, 2 + fd.num_dc_groups + fd.num_groups, d_lf_words_.p, d_mod_words_.p, d_hf_words_.p,
                   d_group_arena_.p, d_out_.p, d_out_info_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[11], stream_));
-  CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   launches_ = g_kernel_launches;
   in_flight_ = true;
   return true;
@@ -374,6 +376,7 @@ bool Encoder::Finish(jxlb200_stats* stats, std::string* err) {
     cudaEventElapsedTime(&ms, ev_[0], ev_[11]); stats->total_ms = ms;
     stats->codestream_bytes = codestream_bytes_;
     stats->bpp = 8.0 * (double)codestream_bytes_ / ((double)fd.xsize * fd.ysize);
+    for (int i = 0; i < 27; ++i) stats->acs_histogram[i] = (uint32_t)h_out_info_[8 + i];
     stats->num_tokens = h_out_info_[4];
     stats->num_clusters = (uint32_t)h_out_info_[5];
   }

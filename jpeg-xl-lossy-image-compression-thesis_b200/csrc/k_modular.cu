@@ -33,13 +33,16 @@ __device__ __forceinline__ int find_dg(const DcGroupInfo* __restrict__ dgs, int 
 __global__ void __launch_bounds__(1024) k_mod_ranks(const uint8_t* __restrict__ acs, const int32_t* __restrict__ raw_qf,
                                                     FrameDim fd, const DcGroupInfo* __restrict__ dgs,
                                                     int32_t* __restrict__ strat_c, int32_t* __restrict__ qf_c,
-                                                    uint32_t* __restrict__ first_count) {
+                                                    uint32_t* __restrict__ first_count,
+                                                    unsigned long long* __restrict__ acs_hist) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_acs_hist[32];   // first blocks per AcStrategy code (jxlb200_stats.acs_histogram)
   const DcGroupInfo d = dgs[blockIdx.x];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int total = d.w * d.h;
   if (t == 0) s_carry = 0;
+  if (t < 32) s_acs_hist[t] = 0;
   __syncthreads();
   // 4 consecutive raster positions per thread and iteration (their loads are issued together)
   for (int i0 = 0; i0 < total; i0 += 4096) {
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(1024) k_mod_ranks(const uint8_t* __restrict__ 
       if (a[u] & 0x80) {
         strat_c[d.block_base + base] = a[u] & 0x7f;
         qf_c[d.block_base + base] = raw_qf[bi[u]] - 1;
+        atomicAdd(&s_acs_hist[a[u] & 31], 1u);
         ++base;
       }
     }
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(1024) k_mod_ranks(const uint8_t* __restrict__ 
     __syncthreads();
   }
   if (t == 0) first_count[blockIdx.x] = s_carry;
+  if (t < 27 && s_acs_hist[t]) atomicAdd(&acs_hist[t], (unsigned long long)s_acs_hist[t]);
 }
 
 // ---- tokens (leaf << 24 | packed residual) + per-leaf histograms
@@ -356,9 +361,9 @@ __global__ void __launch_bounds__(256) k_mod_write(const uint32_t* __restrict__ 
 
 // ------------------------------------------------------------------------------------------ launchers
 void launch_mod_ranks(const uint8_t* acs, const int32_t* raw_qf, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
-                      int32_t* strat_c, int32_t* qf_c, uint32_t* first_count, cudaStream_t s) {
+                      int32_t* strat_c, int32_t* qf_c, uint32_t* first_count, unsigned long long* acs_hist, cudaStream_t s) {
   ++g_kernel_launches;
-  k_mod_ranks<<<num_dg, 1024, 0, s>>>(acs, raw_qf, fd, dgs, strat_c, qf_c, first_count);
+  k_mod_ranks<<<num_dg, 1024, 0, s>>>(acs, raw_qf, fd, dgs, strat_c, qf_c, first_count, acs_hist);
 }
 void launch_mod_tokens(const int16_t* dc_quant, const int8_t* cmap, const int32_t* strat_c, const int32_t* qf_c,
                        const uint32_t* first_count, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,

@@ -64,7 +64,7 @@ void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, con
 // K11 (k_modular.cu)
 void launch_tree_blob(int num_dc_groups, uint32_t* tree_words, uint32_t* tree_bits, cudaStream_t s);
 void launch_mod_ranks(const uint8_t* acs, const int32_t* raw_qf, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
-                      int32_t* strat_c, int32_t* qf_c, uint32_t* first_count, cudaStream_t s);
+                      int32_t* strat_c, int32_t* qf_c, uint32_t* first_count, unsigned long long* acs_hist, cudaStream_t s);
 void launch_mod_tokens(const int16_t* dc_quant, const int8_t* cmap, const int32_t* strat_c, const int32_t* qf_c,
                        const uint32_t* first_count, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,
                        uint32_t total_elems, uint32_t* tokens, uint32_t* mod_hist, cudaStream_t s);

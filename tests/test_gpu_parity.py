@@ -255,3 +255,17 @@ def test_gpu_codestream_decodes_to_the_image(pkg, oracle, encoder):
         p = 10.0 * np.log10(255.0 ** 2 / mse)
         assert floor < p < prev, (d, p)
         prev = p
+
+
+def test_full_size_search_codestream_equals_oracle(pkg, oracle, encoder):
+    """BASELINE config 2/3 scale with the full search: the 3840x2160 codestream of the combined proposal is
+    byte-identical to the oracle's (4 DC groups, 135 AC groups, every transform size)."""
+    img = pkg.synth_image(3840, 2160, 2)
+    data, st = encoder.encode(img, 1.0, 7, pkg.PROPOSAL_COMBINED, 0)
+    ref = oracle.encode(img, 1.0, 7, pkg.PROPOSAL_COMBINED, 0)
+    assert np.array_equal(encoder.dump("acs"), ref.dump("acs"))
+    assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ref.dump("codestream"))
+    acs = encoder.dump("acs")
+    first = acs[acs >= 128] & 0x7F
+    assert [int((first == s).sum()) for s in range(27)] == list(st.acs_histogram)   # stats report the partition
+    assert sum(1 for c in st.acs_histogram if c) >= 6

@@ -29,6 +29,8 @@ void* jxo_decode(const uint8_t* data, size_t size) {
 }
 // reconstructs h*w*3 sRGB bytes from a decoded frame (jxo_decode); returns 1 on success
 int jxo_reconstruct(void* h, uint8_t* rgb) { return ReconstructRgb(*(Frame*)h, rgb) ? 1 : 0; }
+// per-channel sum of squared errors of the frame's reconstruction against the original image
+int jxo_sse(void* h, const uint8_t* orig, size_t stride, uint64_t* sse3) { return ReconstructionSse(*(Frame*)h, orig, stride, sse3) ? 1 : 0; }
 const char* jxo_error(void* h) { return ((Frame*)h)->error.c_str(); }
 void jxo_free(void* h) { delete (Frame*)h; }
 

@@ -40,6 +40,8 @@ class Oracle:
         lib.jxo_decode.argtypes = [vp, ctypes.c_size_t]
         lib.jxo_reconstruct.restype = ctypes.c_int
         lib.jxo_reconstruct.argtypes = [vp, vp]
+        lib.jxo_sse.restype = ctypes.c_int
+        lib.jxo_sse.argtypes = [vp, vp, ctypes.c_size_t, vp]
         lib.jxo_error.restype = ctypes.c_char_p
         lib.jxo_error.argtypes = [vp]
         lib.jxo_free.argtypes = [vp]
@@ -136,6 +138,13 @@ class Frame:
         self.o, self.h = oracle, handle
         err = oracle.lib.jxo_error(handle)
         self.error = err.decode() if err else ""
+
+    def sse(self, image):
+        """per-channel sum of squared errors of this frame's reconstruction against `image` (h, w, 3) uint8"""
+        image = np.ascontiguousarray(image)
+        out = np.zeros(3, dtype=np.uint64)
+        ok = self.o.lib.jxo_sse(self.h, image.ctypes.data, image.strides[0], out.ctypes.data)
+        return out if ok else None
 
     def dump(self, stage):
         sid = STAGE_ID[stage] if isinstance(stage, str) else int(stage)

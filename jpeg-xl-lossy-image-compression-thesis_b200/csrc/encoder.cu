@@ -42,14 +42,11 @@ bool Encoder::Init(int device, std::string* err) {
     CUDA_OK(cudaMemcpy(d_dequant_[k].p, dq.data(), dq.size() * 4, cudaMemcpyHostToDevice));
   }
   {
-    std::vector<float> w8, dq8;
-    host_quant_weights(0, &w8);
-    dq8.resize(64);
-    for (int i = 0; i < 64; ++i) dq8[i] = 1.0f / w8[64 + i];
-    if (!dct8_v2_upload_tables(w8.data(), dq8.data())) { *err = "constant upload"; return false; }
-    // default: 8 lanes per block (k_dct_quant.cu, 0.102 ms per 4K frame); the thread-per-block design
-    // (k_dct8_v2.cu) measured 0.120 ms and is kept as an opt-in for comparison
-    dct8_v1_ = getenv("JXLB200_DCT8_V2") == nullptr;
+    // default: two threads per block with cp.async-staged tiles (k_dct8_v4.cu); JXLB200_DCT8=1 selects the first
+    // design (8 lanes per block, k_dct_quant.cu) for comparison
+    if (const char* e = getenv("JXLB200_DCT8")) dct8_variant_ = atoi(e);
+    if (const char* e = getenv("JXLB200_DCT8_ROWS")) dct8_rows_ = atoi(e);
+    if (const char* e = getenv("JXLB200_DCT8_TPS")) dct8_tps_ = atoi(e);
   }
   {
     std::vector<uint16_t> order;
@@ -58,6 +55,12 @@ bool Encoder::Init(int device, std::string* err) {
     for (int k = 0; k < 64; ++k) izz[order[k]] = (uint8_t)k;
     if (!d_izz8_.Reserve(64)) { *err = "alloc"; return false; }
     CUDA_OK(cudaMemcpy(d_izz8_.p, izz, 64, cudaMemcpyHostToDevice));
+    std::vector<float> bias(dct8_v4_bias_entries());
+    std::vector<uint8_t> lut(2 * 4 * 256);
+    dct8_v4_host_tables(izz, bias.data(), lut.data());
+    if (!d_bias8_.Reserve(bias.size()) || !d_lastlut8_.Reserve(lut.size())) { *err = "alloc"; return false; }
+    CUDA_OK(cudaMemcpy(d_bias8_.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_lastlut8_.p, lut.data(), lut.size(), cudaMemcpyHostToDevice));
   }
   {
     // Q20 log2 table of the clustering cost (same expression as the oracle's Log2Q20)
@@ -102,7 +105,7 @@ void Encoder::Destroy() {
   if (stream_) cudaStreamSynchronize(stream_);
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); }
-  d_izz8_.Release(); d_cvx_.Release(); d_cvy_.Release();
+  d_izz8_.Release(); d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 13; ++o) d_inv_order_[o].Release();
   d_rgb_.Release(); d_xyb_.Release(); d_mask1x1_.Release(); d_pre_.Release(); d_qf_.Release(); d_mask_.Release();
   d_homog_.Release(); d_acs_entropy_.Release(); d_acs_.Release(); d_raw_qf_.Release(); d_cmap_.Release();
@@ -285,13 +288,14 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
                          p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
                          stream_);
   } else {
-    if (dct8_v1_)
+    if (dct8_variant_ == 4)
+      launch_dct8_quant_v4(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_bias8_.p, d_lastlut8_.p, d_cmap_.p,
+                           x_qm_mul_, b_qm_mul_, p.effort >= 5 ? 1 : 0, dct8_rows_, dct8_tps_, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p,
+                           d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
+    else
       launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
                         b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
                         d_nzcount_.p, d_lastk_.p, stream_);
-    else
-      launch_dct8_quant_v2(X, Y, B, fd, d_q_.p, d_cmap_.p, x_qm_mul_, b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p,
-                           d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
   // K8: tokens + per-context histograms

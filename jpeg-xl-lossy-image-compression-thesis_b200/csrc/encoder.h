@@ -48,7 +48,7 @@ class Encoder {
   bool Reserve(const FrameDim& fd, std::string* err);
   bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
   bool in_flight_ = false;
-  bool dct8_v1_ = false;
+  int dct8_variant_ = 4, dct8_rows_ = 2, dct8_tps_ = 512;   // DCT8 kernel: 4 = two threads per block (default), 1 = 8 lanes per block
   int ans_groups_per_warp_ = 1;
   unsigned launches_ = 0;
 
@@ -66,6 +66,8 @@ class Encoder {
   DevBuf<float> d_weights_[17];
   DevBuf<float> d_dequant_[17];
   DevBuf<uint8_t> d_izz8_;        // DCT8: position -> scan index
+  DevBuf<float> d_bias8_;         // k_dct8_v4: Y dequantisation bias per |q|
+  DevBuf<uint8_t> d_lastlut8_;    // k_dct8_v4: last scan index per (lane half, mask byte, byte value)
   DevBuf<uint16_t> d_inv_order_[13];  // per order class: coefficient position -> scan index
   DevBuf<uint8_t> d_cvx_, d_cvy_;
   // per-frame arenas

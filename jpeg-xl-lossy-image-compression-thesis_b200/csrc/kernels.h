@@ -24,11 +24,14 @@ void launch_dct8_quant(const float* x, const float* y, const float* b, const Fra
                        float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
                        uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
 
-// K7, DCT8 frames, thread-per-block design (k_dct8_v2.cu)
-bool dct8_v2_upload_tables(const float* weights192, const float* dequant_y64);
-void launch_dct8_quant_v2(const float* x, const float* y, const float* b, const FrameDim& fd, const QuantDev* qd,
-                          const int8_t* cmap, float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs,
-                          int16_t* dc_quant, uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
+// K7, DCT8 frames, two threads per block with cp.async-staged tiles (k_dct8_v4.cu)
+int dct8_v4_bias_entries();
+void dct8_v4_host_tables(const uint8_t* izz64, float* bias, uint8_t* last_lut /* [2][4][256] */);
+void launch_dct8_quant_v4(const float* x, const float* y, const float* b, const FrameDim& fd, const QuantDev* qd,
+                          const float* weights, const float* dequant_y, const float* bias_tab, const uint8_t* last_lut,
+                          const int8_t* cmap, float x_qm_mul, float b_qm_mul, int adjust, int rows_per_cta, int threads_per_sm,
+                          int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant, uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk,
+                          cudaStream_t s);
 // K6 (k_acs.cu) / K7 general (k_coeff.cu)
 struct AcsParams {
   float info_loss_multiplier, zeros_mul, cost_delta, distance, mul8x8, cmap_x, cmap_b;

@@ -43,7 +43,7 @@ WORKLOADS = {
 STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
 # DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), per workload kernel;
 # filled from profiles/ (None = not captured for this kernel)
-TRAFFIC_BYTES = {"coeff": 128.3e6}   # profiles/r01d_hbm_kernels_full.txt: 100.1 MB read + 28.2 MB written
+TRAFFIC_BYTES = {"coeff": 121.1e6}   # profiles/r01e_dct8_v4_full.txt: 100.1 MB read + 21.0 MB written (k_dct8_quant_v4)
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=64, help="images per rank per step")
+    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (64: 22.2 GP/s, 256: 25.6 GP/s — the "
+                    "pipeline's fill and drain, ~4 ms of rANS latency per image, amortise over the step)")
     ap.add_argument("--pipelines", type=int, default=32, help="images in flight per rank (CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -271,7 +272,7 @@ def main():
         e2e_value = world * B * mp * args.steps / e2e_s
         mean_stage = np.mean(np.array(stage_ms), axis=0)
         peak, peak_kind = measured_peak_gbs()
-        # the HBM-bound kernel the north star names: transform + quantise (k_dct8_quant, 18.3 B/px)
+        # the HBM-bound kernel the north star names: transform + quantise (k_dct8_quant_v4, 18.3 B/px)
         dom = "coeff"
         dom_ms = float(mean_stage[STAGE_INDEX[dom]])
         achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -280,7 +281,7 @@ def main():
             t_ms = float(mean_stage[STAGE_INDEX[sname]])
             per_stage[sname] = {"ms": t_ms, "GB/s": bpp_alg * w * h / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0,
                                 "frac": (bpp_alg * w * h / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else 0.0}
-        roof = {"bound": "hbm", "kernel": "k_dct8_quant (transform + quantise)", "achieved": achieved, "peak": peak,
+        roof = {"bound": "hbm", "kernel": "k_dct8_quant_v4 (transform + quantise)", "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get(dom),
                 "algorithmic_bytes_per_launch": STAGE_BYTES_PER_PX[dom] * w * h, "kernel_ms": dom_ms,
                 "hbm_stages": per_stage,

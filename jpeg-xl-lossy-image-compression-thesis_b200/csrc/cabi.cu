@@ -23,6 +23,7 @@ struct jxlb200_ctx {
   std::vector<Encoder*> extra;        // pipelines 1..P-1, created on first batch use
   int device = 0;
   int num_pipelines = 4;
+  int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
   int ans_gpw = 3;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::string err;
   Encoder* pipe(int i) { return i == 0 ? &enc : extra[i - 1]; }
@@ -58,6 +59,7 @@ jxlb200_ctx* jxlb200_create(int device) {
   jxlb200_ctx* ctx = new jxlb200_ctx();
   ctx->device = device;
   if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->num_pipelines = v; }
+  if (const char* env = getenv("JXLB200_ANS_WARPS")) { const int v = atoi(env); if (v == 16 || v == 32) ctx->ans_warps = v; }
   if (const char* env = getenv("JXLB200_ANS_GPW")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->ans_gpw = v; }
   std::string e;
   if (!ctx->enc.Init(device, &e)) { delete ctx; return nullptr; }
@@ -147,6 +149,7 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
+    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : 16);
     if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
       rc = fail(ctx, e);
       break;
@@ -194,6 +197,7 @@ int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
+    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : 16);
     const auto tq0 = std::chrono::steady_clock::now();
     if (!ctx->pipe(p)->EnqueueDevice(d_pixels[i], (int)widths[i], (int)heights[i], strides[i], ep, &e)) { rc = fail(ctx, e); break; }
     enqueue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();

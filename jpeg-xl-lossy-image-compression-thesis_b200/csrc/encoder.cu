@@ -312,7 +312,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   // K10: one rANS stream per AC group
   const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
   launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_num_clusters, d_small_.p + 4,
-                    ans_groups_per_warp_, d_group_arena_.p, d_group_start_.p, fd.num_groups, stream_);
+                    ans_groups_per_warp_, ans_warps_, d_group_arena_.p, d_group_start_.p, fd.num_groups, stream_);
   CUDA_OK(cudaEventRecord(ev_[9], stream_));
   // K11: modular DC + AC metadata streams, LfGlobal
   uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;

@@ -43,13 +43,14 @@ class Encoder {
   cudaStream_t stream() const { return stream_; }
   // 1 = lowest latency (one group per warp); > 1 packs the rANS chains onto fewer SMs (batch throughput)
   void set_ans_groups_per_warp(int n) { ans_groups_per_warp_ = n; }
+  void set_ans_warps(int n) { ans_warps_ = n; }
 
  private:
   bool Reserve(const FrameDim& fd, std::string* err);
   bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
   bool in_flight_ = false;
   int dct8_variant_ = 4, dct8_rows_ = 2, dct8_tps_ = 512;   // DCT8 kernel: 4 = two threads per block (default), 1 = 8 lanes per block
-  int ans_groups_per_warp_ = 1;
+  int ans_groups_per_warp_ = 1, ans_warps_ = 16;
   unsigned launches_ = 0;
 
   int device_ = -1;

@@ -424,9 +424,9 @@ __global__ void __launch_bounds__(32) k_ans_tables(const uint32_t* __restrict__ 
 // pieces are placed by a warp prefix sum and ORed into a 34-word shared staging window that is
 // stored with coalesced 32-bit writes.  The stream is produced back to front and ENDS at word
 // kTokensPerGroupMax of the group's arena; start_bit[g] = position of its first bit.
-constexpr int kAnsWarps = 16;
 constexpr int kStageWords = 34;
 
+template <int kAnsWarps>
 __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* __restrict__ tokens,
                                                                const uint32_t* __restrict__ token_counts,
                                                                const uint8_t* __restrict__ cmap_g,
@@ -614,21 +614,31 @@ void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t
                                            hdr_bits, hdr_len);
 }
 
-void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
-                       const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
-                       uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
-  static bool configured = false;
+template <int kAnsWarps>
+static void launch_ans_groups_w(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
+                                const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
+                                uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
   const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
                       kAnsWarps * kStageWords * 4;
-  if (!configured) {
-    cudaFuncSetAttribute(k_ans_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
-  ++g_kernel_launches;
+  cudaFuncSetAttribute(k_ans_groups<kAnsWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int per_cta = kAnsWarps * (groups_per_warp < 1 ? 1 : groups_per_warp);
   cudaMemsetAsync(work_counter, 0, 4, s);
-  k_ans_groups<<<(num_groups + per_cta - 1) / per_cta, kAnsWarps * 32, smem, s>>>(
+  k_ans_groups<kAnsWarps><<<(num_groups + per_cta - 1) / per_cta, kAnsWarps * 32, smem, s>>>(
       tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, num_clusters, num_groups, work_counter, out_arena, start_bit);
+}
+
+// warps_per_cta: 16 for a single image (lowest latency: the chains spread over more SMs), 32 in batch mode (a CTA holds
+// the whole SM's shared memory for its reverse maps, so twice the chains per CTA halves the SM time of the stage)
+void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
+                       const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
+                       int warps_per_cta, uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
+  ++g_kernel_launches;
+  if (warps_per_cta >= 32)
+    launch_ans_groups_w<32>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
+                            start_bit, num_groups, s);
+  else
+    launch_ans_groups_w<16>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
+                            start_bit, num_groups, s);
 }
 
 int cluster_num_clusters_offset() { return (int)offsetof(ClusterState, num_clusters); }

@@ -63,7 +63,7 @@ void launch_ans_tables(const uint32_t* cluster_hist, const void* state, uint16_t
                        uint32_t* hdr_bits, uint32_t* hdr_len, cudaStream_t s);
 void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
                        const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
-                       uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s);
+                       int warps_per_cta, uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s);
 // K11 (k_modular.cu)
 void launch_tree_blob(int num_dc_groups, uint32_t* tree_words, uint32_t* tree_bits, cudaStream_t s);
 void launch_mod_ranks(const uint8_t* acs, const int32_t* raw_qf, const FrameDim& fd, const DcGroupInfo* dgs, int num_dg,

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define JXLB200_ABI_VERSION 1
+#define JXLB200_ABI_VERSION 2
 
 typedef struct jxlb200_ctx jxlb200_ctx;
 
@@ -46,6 +46,7 @@ enum {
 /* flags */
 #define JXLB200_FLAG_FIXED_DCT8 1u /* skip the AC-strategy search: DCT8 everywhere (BASELINE config 2) */
 #define JXLB200_FLAG_UNIFORM_QF 2u /* skip the adaptive quant field: qf = 0.841/distance everywhere   */
+#define JXLB200_FLAG_QUALITY 4u    /* also reconstruct the coded frame on the device and fill stats.sse / stats.psnr  */
 
 /* Input image: 8-bit sRGB, interleaved RGB, row-major (what the harness hands to cjxl
  * as a PNG; image_reader.rs ColorType::Rgb8).  `stride` is bytes per row (>= 3*width). */
@@ -78,12 +79,18 @@ typedef struct {
   float stage_ms[16];           /* CUDA-event time per pipeline stage (JXLB200_T_*) */
   float total_ms;               /* device time H2D .. D2H                          */
   uint32_t kernel_launches;     /* CUDA kernels launched by this encode            */
+  /* JXLB200_FLAG_QUALITY: squared error of the decoded 8-bit sRGB image against the input, summed per channel
+   * (R, G, B), and the PSNR over all samples — calculate_mse / calculate_psnr of the harness
+   * (benchmark-jpegxl/src/image_reader.rs:555-606) without the djxl round trip. */
+  uint32_t quality_valid;
+  uint64_t sse[3];
+  double psnr;
 } jxlb200_stats;
 
 enum {
   JXLB200_T_H2D = 0, JXLB200_T_XYB = 1, JXLB200_T_AQ = 2, JXLB200_T_HOMOG = 3, JXLB200_T_ACS = 4,
   JXLB200_T_COEFF = 5, JXLB200_T_TOKENIZE = 6, JXLB200_T_HISTO = 7, JXLB200_T_ANS = 8,
-  JXLB200_T_DC = 9, JXLB200_T_ASSEMBLE = 10, JXLB200_T_D2H = 11
+  JXLB200_T_DC = 9, JXLB200_T_ASSEMBLE = 10, JXLB200_T_D2H = 11, JXLB200_T_QUALITY = 12
 };
 
 /* Intermediate taps for parity tests (same ids in oracle/jxo_frame.h). */

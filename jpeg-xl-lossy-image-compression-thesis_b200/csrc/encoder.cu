@@ -31,6 +31,12 @@ bool Encoder::Init(int device, std::string* err) {
   host_srgb_lut(lut);
   if (!d_lut_.Reserve(256)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_lut_.p, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  {
+    float tab[264];
+    host_recon_tables(tab);
+    if (!d_recon_tab_.Reserve(264)) { *err = "alloc"; return false; }
+    CUDA_OK(cudaMemcpy(d_recon_tab_.p, tab, sizeof(tab), cudaMemcpyHostToDevice));
+  }
   for (int k = 0; k < 17; ++k) {
     std::vector<float> w;
     host_quant_weights(k, &w);
@@ -342,6 +348,15 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   launch_assemble(d_sections_.p, 2 + fd.num_dc_groups + fd.num_groups, d_lf_words_.p, d_mod_words_.p, d_hf_words_.p,
                   d_group_arena_.p, d_out_.p, d_out_info_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[11], stream_));
+  // K13 (optional): reconstruction error of the coded frame against the input, for stats.sse / stats.psnr
+  if (p.flags & JXLB200_FLAG_QUALITY) {
+    const uint16_t* inv_order[13];
+    for (int o = 0; o < 13; ++o) inv_order[o] = d_inv_order_[o].p;
+    launch_recon_sse(fd, d_q_.p, tables, inv_order, d_cmap_.p, 1.0f / powf(1.25f, (float)(x_qm_scale_ - 2)),
+                     1.0f / powf(1.25f, (float)(b_qm_scale_ - 2)), d_acs_.p, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_rgb, stride,
+                     d_recon_tab_.p, d_out_info_.p + 36, stream_);
+  }
+  CUDA_OK(cudaEventRecord(ev_[12], stream_));
   CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
   launches_ = g_kernel_launches;
   in_flight_ = true;
@@ -377,7 +392,15 @@ bool Encoder::Finish(jxlb200_stats* stats, std::string* err) {
     cudaEventElapsedTime(&ms, ev_[8], ev_[9]); stats->stage_ms[JXLB200_T_ANS] = ms;
     cudaEventElapsedTime(&ms, ev_[9], ev_[10]); stats->stage_ms[JXLB200_T_DC] = ms;
     cudaEventElapsedTime(&ms, ev_[10], ev_[11]); stats->stage_ms[JXLB200_T_ASSEMBLE] = ms;
-    cudaEventElapsedTime(&ms, ev_[0], ev_[11]); stats->total_ms = ms;
+    cudaEventElapsedTime(&ms, ev_[11], ev_[12]); stats->stage_ms[JXLB200_T_QUALITY] = ms;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[12]); stats->total_ms = ms;
+    if (params_.flags & JXLB200_FLAG_QUALITY) {
+      stats->quality_valid = 1;
+      double sum = 0.0;
+      for (int k = 0; k < 3; ++k) { stats->sse[k] = h_out_info_[36 + k]; sum += (double)stats->sse[k]; }
+      const double mse = sum / (3.0 * (double)fd.xsize * (double)fd.ysize);
+      stats->psnr = mse > 0.0 ? 10.0 * log10(255.0 * 255.0 / mse) : INFINITY;
+    }
     stats->codestream_bytes = codestream_bytes_;
     stats->bpp = 8.0 * (double)codestream_bytes_ / ((double)fd.xsize * fd.ysize);
     for (int i = 0; i < 27; ++i) stats->acs_histogram[i] = (uint32_t)h_out_info_[8 + i];

@@ -55,7 +55,7 @@ class Encoder {
 
   int device_ = -1;
   cudaStream_t stream_ = nullptr;
-  cudaEvent_t ev_[16] = {};
+  cudaEvent_t ev_[16] = {};   // ev_[12] closes the optional quality stage
   FrameDim fd_{};
   EncodeParams params_{};
   bool have_frame_ = false;
@@ -63,7 +63,7 @@ class Encoder {
   int x_qm_scale_ = 2, b_qm_scale_ = 2;
 
   // constant tables
-  DevBuf<float> d_lut_;
+  DevBuf<float> d_lut_, d_recon_tab_;
   DevBuf<float> d_weights_[17];
   DevBuf<float> d_dequant_[17];
   DevBuf<uint8_t> d_izz8_;        // DCT8: position -> scan index

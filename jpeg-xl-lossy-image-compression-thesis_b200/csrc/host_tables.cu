@@ -33,6 +33,31 @@ void host_srgb_lut(float lut[256]) {
   }
 }
 
+// tab[0..8]: inverse opsin matrix (computed in double from the forward matrix, rounded to float);
+// tab[9 + n]: sRGB code boundary in linear light, EOTF((n + 0.5) / 255) by the encoder's rational polynomial —
+// code n is chosen when boundary[n-1] <= linear < boundary[n] (oracle/jxo_recon.cc SrgbBoundaries / InverseOpsin)
+void host_recon_tables(float tab[264]) {
+  const double M[3][3] = {{0.30, 0.622, 0.078}, {0.23, 0.692, 0.078}, {0.24342268924547819, 0.20476744424496821, 0.55180986650955360}};
+  const double a = M[0][0], b = M[0][1], c = M[0][2], d = M[1][0], e = M[1][1], g = M[1][2], h = M[2][0], i = M[2][1], j = M[2][2];
+  const double det = a * (e * j - g * i) - b * (d * j - g * h) + c * (d * i - e * h);
+  const double v[9] = {(e * j - g * i) / det, (c * i - b * j) / det, (b * g - c * e) / det,
+                       (g * h - d * j) / det, (a * j - c * h) / det, (c * d - a * g) / det,
+                       (d * i - e * h) / det, (b * h - a * i) / det, (a * e - b * d) / det};
+  for (int k = 0; k < 9; ++k) tab[k] = (float)v[k];
+  static const float p[5] = {2.200248328e-04f, 1.043637593e-02f, 1.624820318e-01f, 7.961564959e-01f, 8.210152774e-01f};
+  static const float q[5] = {2.631846970e-01f, 1.076976492e+00f, 4.987528350e-01f, -5.512498495e-02f, 6.521209011e-03f};
+  for (int n = 0; n < 255; ++n) {
+    const float x = ((float)n + 0.5f) / 255.0f;
+    if (x > 0.04045f) {
+      float yp = p[4], yq = q[4];
+      for (int k = 3; k >= 0; --k) { yp = fmaf(yp, x, p[k]); yq = fmaf(yq, x, q[k]); }
+      tab[9 + n] = yp / yq;
+    } else {
+      tab[9 + n] = x * (1.0f / 12.92f);
+    }
+  }
+}
+
 static float h_log2(float x) {
   const int32_t xb = (int32_t)fbits(x);
   const int32_t es = (xb - 0x3f2aaaab) >> 23;

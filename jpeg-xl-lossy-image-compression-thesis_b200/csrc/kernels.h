@@ -45,6 +45,12 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
                           uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
 
+// K13 (k_recon.cu): per-channel sum of squared errors of the coded frame's reconstruction against the input pixels
+void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order,
+                      const int8_t* cmap, float inv_qm_x, float inv_qm_b, const uint8_t* acs, const int32_t* raw_qf,
+                      const int16_t* coeffs, const int16_t* dc_quant, const uint8_t* rgb, size_t stride, const float* tables,
+                      unsigned long long* sse3, cudaStream_t s);
+
 // ---- entropy stage -------------------------------------------------------------------------
 // one 2048x2048 DC group: rectangle in blocks, its 64x64-tile rectangle, first element / first block slot
 struct DcGroupInfo { int x0, y0, w, h, tw, th; uint32_t elem_base; uint32_t block_base; };

@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY, PROPOSAL_COMBINED = 0, 1, 2, 3
-FLAG_FIXED_DCT8, FLAG_UNIFORM_QF = 1, 2
+FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY = 1, 2, 4
 
 # stage id -> (name, numpy dtype)   (JXLB200_STAGE_* in include/jxlb200.h)
 STAGES = {
@@ -52,7 +52,8 @@ class _Stats(ctypes.Structure):
                 ("height", ctypes.c_uint32), ("num_groups", ctypes.c_uint32), ("num_dc_groups", ctypes.c_uint32),
                 ("global_scale", ctypes.c_uint32), ("quant_dc", ctypes.c_uint32), ("num_tokens", ctypes.c_uint64),
                 ("num_clusters", ctypes.c_uint32), ("acs_histogram", ctypes.c_uint32 * 27),
-                ("stage_ms", ctypes.c_float * 16), ("total_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32)]
+                ("stage_ms", ctypes.c_float * 16), ("total_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32),
+                ("quality_valid", ctypes.c_uint32), ("sse", ctypes.c_uint64 * 3), ("psnr", ctypes.c_double)]
 
 
 @dataclass
@@ -71,12 +72,15 @@ class Stats:
     stage_ms: list = field(default_factory=list)
     total_ms: float = 0.0
     kernel_launches: int = 0
+    sse: Optional[list] = None      # FLAG_QUALITY: per-channel squared error of the decoded image against the input
+    psnr: Optional[float] = None    # FLAG_QUALITY: PSNR over all samples, dB
 
     @classmethod
     def _from_c(cls, s: _Stats) -> "Stats":
         return cls(int(s.codestream_bytes), float(s.bpp), int(s.width), int(s.height), int(s.num_groups),
                    int(s.num_dc_groups), int(s.global_scale), int(s.quant_dc), int(s.num_tokens),
-                   int(s.num_clusters), list(s.acs_histogram), list(s.stage_ms), float(s.total_ms), int(s.kernel_launches))
+                   int(s.num_clusters), list(s.acs_histogram), list(s.stage_ms), float(s.total_ms), int(s.kernel_launches),
+                   [int(v) for v in s.sse] if s.quality_valid else None, float(s.psnr) if s.quality_valid else None)
 
 
 def library_path() -> str:

@@ -269,3 +269,35 @@ def test_full_size_search_codestream_equals_oracle(pkg, oracle, encoder):
     first = acs[acs >= 128] & 0x7F
     assert [int((first == s).sum()) for s in range(27)] == list(st.acs_histogram)   # stats report the partition
     assert sum(1 for c in st.acs_histogram if c) >= 6
+
+
+@pytest.mark.parametrize("w,h,proposal,flags", [(256, 200, 3, 0), (512, 384, 0, 1), (131, 77, 1, 0), (640, 480, 2, 0)])
+def test_quality_stats_equal_oracle(pkg, oracle, encoder, w, h, proposal, flags):
+    """FLAG_QUALITY: the device reconstructs the frame it coded (dequantise, DC -> LLF, chroma-from-luma, inverse
+    transforms of every strategy, XYB -> 8-bit sRGB) and returns the per-channel squared error against the input:
+    bit-exact integers against oracle/jxo_recon.cc; the PSNR follows calculate_psnr (image_reader.rs:604-606)."""
+    img = pkg.synth_image(w, h, 5)
+    for distance in (0.5, 1.0, 3.0):
+        data, st = encoder.encode(img, distance, 7, proposal, flags | pkg.FLAG_QUALITY)
+        f = oracle.encode(img, distance, 7, proposal, flags)
+        assert f.error == ""
+        want = [int(v) for v in f.sse(img)]
+        f.close()
+        assert st.sse == want, (distance, st.sse, want)
+        mse = sum(want) / (3.0 * w * h)
+        assert abs(st.psnr - 10.0 * np.log10(255.0 ** 2 / mse)) < 1e-9
+        # the codestream does not depend on the flag
+        data0, st0 = encoder.encode(img, distance, 7, proposal, flags)
+        assert data0 == data and st0.sse is None
+
+
+def test_quality_stats_batch_and_full_size(pkg, oracle, encoder):
+    """The quality stage inside the pipelined batch path, at 4K (size-independent property: the statistics of an
+    image do not depend on how many others are in flight)."""
+    w, h = 3840, 2160
+    imgs = [pkg.synth_image(w, h, 40 + i) for i in range(3)]
+    single = [encoder.encode(im, 1.0, 7, 0, pkg.FLAG_FIXED_DCT8 | pkg.FLAG_QUALITY)[1] for im in imgs]
+    encoder.set_pipelines(3)
+    datas, sts = encoder.encode_batch(imgs, 1.0, 7, 0, pkg.FLAG_FIXED_DCT8 | pkg.FLAG_QUALITY)
+    for a, b in zip(single, sts):
+        assert a.sse == b.sse and a.psnr == b.psnr and 30.0 < a.psnr < 60.0

@@ -149,3 +149,19 @@ def test_decoded_pixels_proposals_and_edges(pkg, oracle):
     flat = np.full((40, 72, 3), 200, dtype=np.uint8)
     rec = oracle.decode_pixels(oracle.encode(flat, 1.0, 7, 3, 0).dump("codestream").tobytes(), 72, 40)
     assert np.abs(rec.astype(int) - 200).max() <= 1
+
+
+def test_sse_tap_matches_reconstruction(pkg, oracle):
+    """jxo_sse (the checker of the device's quality statistics) is the squared error of jxo_reconstruct's pixels
+    against the input, per channel, over the image area only (ragged sizes: the padding is not counted)."""
+    for (w, h, proposal, flags) in ((200, 120, pkg.PROPOSAL_COMBINED, 0), (96, 64, pkg.PROPOSAL_NONE, pkg.FLAG_FIXED_DCT8),
+                                    (131, 77, pkg.PROPOSAL_PARTITIONING, 0)):
+        img = pkg.synth_image(w, h, 33)
+        f = oracle.encode(img, 1.0, 7, proposal, flags)
+        assert f.error == ""
+        sse = f.sse(img)
+        rec = oracle.decode_pixels(f.dump("codestream").tobytes(), w, h)
+        assert sse is not None and rec is not None
+        d = rec.astype(np.int64) - img.astype(np.int64)
+        assert [int(v) for v in sse] == [int((d[:, :, c] ** 2).sum()) for c in range(3)]
+        f.close()

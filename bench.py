@@ -137,6 +137,38 @@ def cpu_oracle_throughput(workload, budget_images, threads):
     return budget_images * w * h / 1e6 / dt, dt
 
 
+def find_cjxl():
+    """The reference's encoder binary, if one was supplied ($JXLB200_CJXL, baseline/_ref/bin/cjxl, PATH): SURVEY 8d.
+    None in this image (libjxl is cloned from the network inside the reference's Docker build, Dockerfile:40)."""
+    import shutil
+    for cand in (os.environ.get("JXLB200_CJXL"), os.path.join(ROOT, "baseline", "_ref", "bin", "cjxl"), shutil.which("cjxl")):
+        if cand and os.path.isfile(cand) and os.access(cand, os.X_OK):
+            return cand
+    return None
+
+
+def cjxl_throughput(cjxl, workload, n_images, threads):
+    """`cjxl in.ppm out.jxl --distance=D --effort=E` (the reference's call, docker_manager.rs:125-136) on synthetic
+    PPMs, libjxl's own thread pool on `threads` threads, one image after the other."""
+    import tempfile
+    pkg = importlib.import_module(PKG)
+    w, h, dist, effort, proposal, flags = WORKLOADS[workload]
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for i in range(min(n_images, 2)):
+            path = os.path.join(tmp, f"in{i}.ppm")
+            with open(path, "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (w, h))
+                f.write(pkg.synth_image(w, h, 1000 + i).tobytes())
+            paths.append(path)
+        t0 = time.perf_counter()
+        for i in range(n_images):
+            subprocess.run([cjxl, paths[i % len(paths)], os.path.join(tmp, "out.jxl"), f"--distance={dist}", f"--effort={effort}",
+                            f"--num_threads={threads}"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+    return n_images * w * h / 1e6 / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on the host cores.  The reference's own
     encoder (libjxl behind `cjxl`, docker_manager.rs:136) cannot be built or installed offline, so this
@@ -147,9 +179,13 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     w, h, dist, effort, proposal, flags = WORKLOADS[args.workload]
     per_step = max(1, min(cores, 8))
+    cjxl = find_cjxl()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_oracle_throughput(args.workload, per_step, per_step)
+        if cjxl:
+            v, dt = cjxl_throughput(cjxl, args.workload, 4, cores)
+        else:
+            v, dt = cpu_oracle_throughput(args.workload, per_step, per_step)
         if i >= args.warmup:
             vals.append((v, dt))
     value = statistics.mean(v for v, _ in vals)
@@ -160,9 +196,11 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "width": w, "height": h, "distance": dist, "effort": effort,
                    "proposal": proposal, "flags": flags},
-        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": per_step, "kind": "port",
-                         "sample": f"{per_step} images of {w}x{h} per step, one oracle encode per host thread "
-                                   "(own CPU restatement; libjxl/cjxl is not installable offline)"},
+        "cpu_baseline": ({"value": value, "unit": "MP/s", "cores": cores, "kind": "reference",
+                          "sample": f"4 images of {w}x{h} per step through {cjxl} --num_threads={cores}"} if cjxl else
+                         {"value": value, "unit": "MP/s", "cores": per_step, "kind": "port",
+                          "sample": f"{per_step} images of {w}x{h} per step, one oracle encode per host thread "
+                                    "(own CPU restatement; no cjxl binary found: libjxl is not installable offline)"}),
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

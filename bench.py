@@ -325,6 +325,13 @@ def main():
                 "hbm_stages": per_stage,
                 "single_image_stage_ms": {k: float(mean_stage[v]) for k, v in STAGE_INDEX.items()},
                 "single_image_total_ms": float(mean_stage[-1]),
+                "nominal_peak": {"GB/s": 8000.0, "frac": achieved / 8000.0},
+                "entropy_stage": {"kernel": "k_ans_groups (one warp per 256x256 AC group, serial rANS chain)",
+                                  "ms": float(mean_stage[STAGE_INDEX["ans"]]), "tokens": int(last_stats.num_tokens),
+                                  "Mtokens_per_s": (last_stats.num_tokens / 1e6) / (float(mean_stage[STAGE_INDEX["ans"]]) / 1e3)
+                                  if mean_stage[STAGE_INDEX["ans"]] > 0 else 0.0,
+                                  "bound": "dependency latency of the longest group's chain (~126 cycles per token, ncu: "
+                                           "fixed-latency waits 49 %, shared-memory loads 22 %, issue 23 %), not bandwidth"},
                 "note": "per-kernel times from single-image encodes (one stream); the largest stage, the per-group "
                         "rANS chains (ans), is serial-latency bound, not bandwidth bound: see profiles/"}
         line = {
@@ -338,8 +345,10 @@ def main():
                              f"{n_distinct * 3 * w * h >> 20} MiB",
                        "parallelism": f"image-sharded x{world}, no data-path collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": B * 3 * w * h,
-                    "d2h_bytes_per_step": out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps},
+            "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * B * 3 * w * h,
+                    "d2h_bytes_per_step": world * out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "h2d_GBps_per_gpu": B * 3 * w * h / (e2e_s / args.steps) / 1e9,
+                    "note": "bound by the host link: a pinned 256 MiB copy alone reaches 55.5 GB/s on this box"},
             "gpu_launches": launches,
             "roofline": roof,
             "bpp": last_stats.bpp, "codestream_bytes": last_stats.codestream_bytes,

@@ -23,6 +23,8 @@ struct jxlb200_ctx {
   std::vector<Encoder*> extra;        // pipelines 1..P-1, created on first batch use
   int device = 0;
   int num_pipelines = 4;
+  cudaStream_t copy_stream = nullptr; // batch mode: one H2D stream for all pipelines
+  bool use_copy_stream = true;
   int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
   int ans_gpw = 3;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::string err;
@@ -59,6 +61,7 @@ jxlb200_ctx* jxlb200_create(int device) {
   jxlb200_ctx* ctx = new jxlb200_ctx();
   ctx->device = device;
   if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->num_pipelines = v; }
+  if (const char* env = getenv("JXLB200_COPY_STREAM")) ctx->use_copy_stream = atoi(env) != 0;
   if (const char* env = getenv("JXLB200_ANS_WARPS")) { const int v = atoi(env); if (v == 16 || v == 32) ctx->ans_warps = v; }
   if (const char* env = getenv("JXLB200_ANS_GPW")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->ans_gpw = v; }
   std::string e;
@@ -70,6 +73,7 @@ void jxlb200_destroy(jxlb200_ctx* ctx) {
   if (!ctx) return;
   ctx->enc.Destroy();
   for (Encoder* e : ctx->extra) { e->Destroy(); delete e; }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -116,6 +120,7 @@ int jxlb200_encode(jxlb200_ctx* ctx, const jxlb200_image* image, const jxlb200_p
   std::string e;
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
   ctx->enc.set_ans_groups_per_warp(1);
+  ctx->enc.set_copy_stream(nullptr);
   if (!ctx->enc.EncodeHost(image->pixels, (int)image->width, (int)image->height, image->stride, ep, stats, &e))
     return fail(ctx, e);
   if (!ctx->enc.Fetch(out, out_len, &e)) return fail(ctx, e);
@@ -134,6 +139,10 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
   }
   const int P = (int)std::min<size_t>((size_t)ctx->num_pipelines, n ? n : 1);
   if (!ensure_pipelines(ctx, P)) return -1;
+  if (ctx->use_copy_stream && P > 1 && !ctx->copy_stream) {
+    cudaSetDevice(ctx->device);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) ctx->copy_stream = nullptr;
+  }
   std::vector<long> owner(P, -1);   // image currently in flight on each pipeline
   std::string e;
   int rc = 0;
@@ -150,6 +159,7 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
     ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : 16);
+    ctx->pipe(p)->set_copy_stream(P > 1 && ctx->use_copy_stream ? ctx->copy_stream : nullptr);
     if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
       rc = fail(ctx, e);
       break;

@@ -109,6 +109,7 @@ void Encoder::Destroy() {
   if (device_ < 0) return;
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  if (ev_copy_) { cudaEventDestroy(ev_copy_); ev_copy_ = nullptr; }
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); }
   d_izz8_.Release(); d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
@@ -190,8 +191,9 @@ bool Encoder::EnqueueHost(const uint8_t* pixels, int w, int h, size_t stride, co
   const size_t bytes = row * h;
   if (!d_rgb_.Reserve(bytes + 16)) { *err = "device allocation failed"; return false; }
   CUDA_OK(cudaEventRecord(ev_[0], stream_));
+  cudaStream_t cs = copy_stream_ ? copy_stream_ : stream_;
   if (stride == row && IsPinned(pixels)) {
-    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, pixels, bytes, cudaMemcpyHostToDevice, stream_));
+    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, pixels, bytes, cudaMemcpyHostToDevice, cs));
   } else {
     if (bytes > h_pinned_cap_) {
       if (h_pinned_) cudaFreeHost(h_pinned_);
@@ -202,7 +204,12 @@ bool Encoder::EnqueueHost(const uint8_t* pixels, int w, int h, size_t stride, co
     // pack rows into the pinned staging buffer (drops any row padding), then one async copy
     if (stride == row) memcpy(h_pinned_, pixels, bytes);
     else for (int y = 0; y < h; ++y) memcpy(h_pinned_ + (size_t)y * row, pixels + (size_t)y * stride, row);
-    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, h_pinned_, bytes, cudaMemcpyHostToDevice, stream_));
+    CUDA_OK(cudaMemcpyAsync(d_rgb_.p, h_pinned_, bytes, cudaMemcpyHostToDevice, cs));
+  }
+  if (cs != stream_) {
+    if (!ev_copy_) CUDA_OK(cudaEventCreateWithFlags(&ev_copy_, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(ev_copy_, cs));
+    CUDA_OK(cudaStreamWaitEvent(stream_, ev_copy_, 0));
   }
   fd_.Set(w, h);
   return Run(d_rgb_.p, row, p, err);

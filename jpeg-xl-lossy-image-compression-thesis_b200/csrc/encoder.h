@@ -44,6 +44,9 @@ class Encoder {
   // 1 = lowest latency (one group per warp); > 1 packs the rANS chains onto fewer SMs (batch throughput)
   void set_ans_groups_per_warp(int n) { ans_groups_per_warp_ = n; }
   void set_ans_warps(int n) { ans_warps_ = n; }
+  // batch mode: all pipelines send their input over ONE copy stream (whole images back to back on the H2D engine
+  // instead of 32 streams' copies time-sliced against each other); nullptr = copy on the encoder's own stream
+  void set_copy_stream(cudaStream_t s) { copy_stream_ = s; }
 
  private:
   bool Reserve(const FrameDim& fd, std::string* err);
@@ -55,6 +58,8 @@ class Encoder {
 
   int device_ = -1;
   cudaStream_t stream_ = nullptr;
+  cudaStream_t copy_stream_ = nullptr;
+  cudaEvent_t ev_copy_ = nullptr;
   cudaEvent_t ev_[16] = {};   // ev_[12] closes the optional quality stage
   FrameDim fd_{};
   EncodeParams params_{};

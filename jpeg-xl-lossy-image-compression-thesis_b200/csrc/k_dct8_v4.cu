@@ -203,11 +203,13 @@ __device__ __forceinline__ void v4_pack_half(const int q[32], uint32_t keep[16],
 }
 
 // QuantizeBlockAC (DCT8) of the lane's 32 coefficients.  A quantised value is non-zero exactly when
-// |val| >= threshold and |val| > 0.5 (round-half-even), so the non-zero mask comes from two compares.
+// |val| >= threshold and |val| > 0.5 (round-half-even), so the non-zero mask comes from one compare.
 // q holds int32 values (saturated by the conversion); the int16 clamp happens when the words are packed.
 __device__ __forceinline__ uint32_t v4_quantize(const float c[32], int p, const float* __restrict__ w, float qac_mul,
                                                 const float thr[4], int q[32]) {
-  const float t_lo = p ? thr[2] : thr[0], t_hi = p ? thr[3] : thr[1];
+  // |val| > 0.5 is |val| >= the next float above 0.5, so both conditions fold into one threshold per quadrant
+  const float kAboveHalf = 0.50000006f;
+  const float t_lo = fmaxf(p ? thr[2] : thr[0], kAboveHalf), t_hi = fmaxf(p ? thr[3] : thr[1], kAboveHalf);
   uint32_t mask = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -219,7 +221,7 @@ __device__ __forceinline__ uint32_t v4_quantize(const float c[32], int p, const 
         const int x = h * 4 + e;
         const float val = (f4get(w4, e) * qac_mul) * c[j * 8 + x];
         const float a = fabsf(val);
-        bool nonzero = (a >= (h == 0 ? t_lo : t_hi)) && (a > 0.5f);
+        bool nonzero = a >= (h == 0 ? t_lo : t_hi);
         if (j == 0 && x == 0) nonzero = nonzero && (p != 0);
         q[j * 8 + x] = nonzero ? __float2int_rn(val) : 0;
         if (nonzero) mask |= 1u << (j * 8 + x);

@@ -46,11 +46,17 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
                                                   uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_off[3072 + 1];
   __shared__ uint32_t s_warp[8];
+  // first 16 scan positions of each of the warp's 32 entries, fetched by the entry's own lane together with its
+  // metadata (two 16-byte loads in flight per lane) so that the walk below reads them from shared memory instead of
+  // waiting for one dependent 2-byte global load per round
+  __shared__ __align__(16) int16_t s_coef[8][32][16];
   // CTA-private counters of symbols 0 and 1 of every context: those bins take most of the increments
   // (zero coefficients, +-1) and a few of them are so hot that global atomics on them serialise in L2
-  extern __shared__ uint32_t s_hot[];   // [2][kNumAcContexts]
+  // (one word per context: symbol 0 in the low half, symbol 1 in the high half — a CTA emits at most 384 x 64 tokens,
+  // so neither half can overflow; 30 KB instead of 59 KB lets a fourth CTA live on the SM)
+  extern __shared__ uint32_t s_hot[];   // [kNumAcContexts]
   const int g = blockIdx.x, part = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int i = t; i < 2 * kNumAcContexts; i += 256) s_hot[i] = 0;
+  for (int i = t; i < kNumAcContexts; i += 256) s_hot[i] = 0;
   const int gx0 = (g % fd.gxs) * 32, gy0 = (g / fd.gxs) * 32;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   // ---- token count per (block, slot): 12 consecutive entries per thread = 4 blocks
@@ -121,13 +127,20 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
         m_nztok = (ctx << 16) | (uint32_t)nz;
         m_misc = (uint32_t)s | ((uint32_t)block_ctx << 8) | ((uint32_t)nz << 16);
         out[m_off] = m_nztok;
+        if (m_count > 1) {
+          const size_t cblk = (size_t)g * kGroupBlocks + (size_t)ly * 32 + lx;
+          const uint4* src = reinterpret_cast<const uint4*>(coeffs + (cblk * 3 + slot) * 64);
+          uint4* dst = reinterpret_cast<uint4*>(&s_coef[warp][lane][0]);
+          dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
+        }
         uint32_t tok, nb, bits;
         hybrid_encode((uint32_t)nz, tok, nb, bits);
-        if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+        if (tok < 2) atomicAdd(&s_hot[ctx], tok ? 0x10000u : 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
       }
     }
     // coefficient tokens: a (block, channel) has ~4.5 of them on average, so four entries are walked side by side,
     // eight lanes each (the running non-zero count comes from the group's byte of the ballot)
+    __syncwarp();
     unsigned todo = __ballot_sync(0xffffffffu, m_count > 1);
     const int gi = lane >> 3, gl = lane & 7;
     while (todo) {
@@ -157,10 +170,14 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
         const int k = k0 + gl;
         int coef = 0;
         if (k <= last) {
-          const int jj = k >> 6;
-          const int jx = jj % cx, jy = jj / cx;
-          const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
-          coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
+          if (k < 16) {
+            coef = s_coef[warp][src][k];
+          } else {
+            const int jj = k >> 6;
+            const int jx = jj % cx, jy = jj / cx;
+            const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
+            coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
+          }
         }
         const unsigned mask = (__ballot_sync(0xffffffffu, coef != 0) >> (gi * 8)) & 0xFFu;
         const int nz_here = nz - __popc(mask & ((1u << gl) - 1));
@@ -172,17 +189,19 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
           out[off + 1 + (k - n)] = (ctx << 16) | v;
           uint32_t tok, nb, bits;
           hybrid_encode(v, tok, nb, bits);
-          if (tok < 2) atomicAdd(&s_hot[tok * kNumAcContexts + ctx], 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+          if (tok < 2) atomicAdd(&s_hot[ctx], tok ? 0x10000u : 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
         }
         nz -= __popc(mask);
         prev_carry = (int)(mask >> 7);
       }
     }
+    __syncwarp();   // the next round's lanes overwrite s_coef[warp]
   }
   __syncthreads();
-  for (int i = t; i < 2 * kNumAcContexts; i += 256) {
+  for (int i = t; i < kNumAcContexts; i += 256) {
     const uint32_t v = s_hot[i];
-    if (v) { const int tok = i >= kNumAcContexts, ctx = i - tok * kNumAcContexts; atomicAdd(&hist[ctx * kAcAlphabet + tok], v); }
+    if (v & 0xFFFFu) atomicAdd(&hist[i * kAcAlphabet], v & 0xFFFFu);
+    if (v >> 16) atomicAdd(&hist[i * kAcAlphabet + 1], v >> 16);
   }
 }
 
@@ -588,11 +607,11 @@ void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* 
                      cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kNumAcContexts * sizeof(uint32_t)));
+    cudaFuncSetAttribute(k_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNumAcContexts * sizeof(uint32_t)));
     configured = true;
   }
   ++g_kernel_launches;
-  k_tokenize<<<dim3(fd.num_groups, kTokSplit), 256, 2 * kNumAcContexts * sizeof(uint32_t), s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
+  k_tokenize<<<dim3(fd.num_groups, kTokSplit), 256, kNumAcContexts * sizeof(uint32_t), s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
 }
 
 void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,

@@ -1,4 +1,17 @@
-for cs in 1 0; do JXLB200_COPY_STREAM=$cs python bench.py --no-cpu-baseline --steps 5 --warmup 3 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('copy_stream $cs value', round(d['value']), 'e2e', round(d['e2e']['value']), 'e2e ms', round(d['e2e']['ms_per_step'],2), 'GB/s', round(d['e2e']['h2d_bytes_per_step']/d['e2e']['ms_per_step']/1e6,1))"; done
-timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "batch or strided or error" 2>&1 | tail -2
+timeout 1200 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -2
+python tools/exp_dct8.py
+python - <<'PY'
+import sys, importlib
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+pkg = importlib.import_module("jpeg-xl-lossy-image-compression-thesis_b200")
+w, h = 3840, 2160
+d = torch.from_numpy(pkg.synth_image(w, h, 0)).cuda()
+enc = pkg.Encoder(0)
+ts = []
+for i in range(8):
+    st = enc.encode_device(d.data_ptr(), w, h, 3 * w, 1.0, 7, 0, 1)
+    ts.append(st.stage_ms[6])
+print("tokenize ms", np.round(ts[3:], 4))
+PY
+python tools/exp_pipelines.py

@@ -37,7 +37,7 @@ __constant__ uint8_t c_nnz_ctx[64] = {0,   0,   31,  62,  62,  93,  93,  93,  93
                                       206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206, 206};
 
 // ------------------------------------------------------------------------------------------ K8
-constexpr int kTokSplit = 8;   // CTAs per AC group (each recomputes the group's scan, emits 1/8 of the entries)
+constexpr int kTokSplit = 4;   // CTAs per AC group (each recomputes the group's scan, emits 1/4 of the entries)
 
 __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ acs, const uint8_t* __restrict__ nzeros,
                                                   const uint16_t* __restrict__ nzcount, const uint16_t* __restrict__ lastk,
@@ -46,17 +46,19 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
                                                   uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_off[3072 + 1];
   __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_next;
   // first 16 scan positions of each of the warp's 32 entries, fetched by the entry's own lane together with its
   // metadata (two 16-byte loads in flight per lane) so that the walk below reads them from shared memory instead of
   // waiting for one dependent 2-byte global load per round
   __shared__ __align__(16) int16_t s_coef[8][32][16];
   // CTA-private counters of symbols 0 and 1 of every context: those bins take most of the increments
   // (zero coefficients, +-1) and a few of them are so hot that global atomics on them serialise in L2
-  // (one word per context: symbol 0 in the low half, symbol 1 in the high half — a CTA emits at most 384 x 64 tokens,
-  // so neither half can overflow; 30 KB instead of 59 KB lets a fourth CTA live on the SM)
+  // (one word per context: symbol 0 in the low half, symbol 1 in the high half — a CTA emits at most 256 blocks x 3 x 64
+  // = 49 152 tokens, so neither half can overflow; 30 KB instead of 59 KB lets a fourth CTA live on the SM)
   extern __shared__ uint32_t s_hot[];   // [kNumAcContexts]
   const int g = blockIdx.x, part = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int i = t; i < kNumAcContexts; i += 256) s_hot[i] = 0;
+  if (t == 0) s_next = 0;
   const int gx0 = (g % fd.gxs) * 32, gy0 = (g / fd.gxs) * 32;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   // ---- token count per (block, slot): 12 consecutive entries per thread = 4 blocks
@@ -99,13 +101,19 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
   // ---- emit: this CTA's slice of the entries; a warp takes 32 entries at a time, every lane
   // prefetching the metadata of one of them, then the warp walks the 32 entries together
   uint32_t* out = tokens + (size_t)g * kTokensPerGroupMax;
-  constexpr int kPerCta = 3072 / kTokSplit;          // 384
-  constexpr int kPerWarp = kPerCta / 8;              // 48
-  const int e_begin = part * kPerCta + warp * kPerWarp;
-  for (int e0 = e_begin; e0 < e_begin + kPerWarp; e0 += 32) {
+  // Rounds of 32 entries are drawn from a CTA-wide counter: the token count of a round varies by more than 10x with the
+  // content, and a static split left the warps waiting 35 % of the kernel at the final barrier (ncu, profiles/r01g)
+  constexpr int kPerCta = 3072 / kTokSplit;          // 768
+  constexpr int kRounds = kPerCta / 32;              // 24
+  for (;;) {
+    int round = 0;
+    if (lane == 0) round = (int)atomicAdd(&s_next, 1u);
+    round = __shfl_sync(0xffffffffu, round, 0);
+    if (round >= kRounds) break;
+    const int e0 = part * kPerCta + round * 32;
     const int e = e0 + lane;
     uint32_t m_off = 0, m_count = 0, m_nztok = 0, m_misc = 0;   // misc: s | block_ctx << 8 | nz << 16
-    if (e < e_begin + kPerWarp) {
+    {
       m_off = s_off[e];
       m_count = s_off[e + 1] - m_off;
       if (m_count) {

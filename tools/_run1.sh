@@ -1,5 +1,4 @@
 timeout 1200 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -2
-python tools/exp_dct8.py
 python - <<'PY'
 import sys, importlib
 sys.path.insert(0, "/root/repo")

@@ -25,6 +25,7 @@ struct jxlb200_ctx {
   int num_pipelines = 4;
   cudaStream_t copy_stream = nullptr; // batch mode: one H2D stream for all pipelines
   bool use_copy_stream = true;
+  int ans_warps_single = 8;           // warps per rANS CTA for a single image (4: 2.51 ms, 8: 2.45 ms, 16: 2.65 ms per 4K frame) ($JXLB200_ANS_WARPS_SINGLE)
   int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
   int ans_gpw = 3;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::string err;
@@ -62,7 +63,8 @@ jxlb200_ctx* jxlb200_create(int device) {
   ctx->device = device;
   if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->num_pipelines = v; }
   if (const char* env = getenv("JXLB200_COPY_STREAM")) ctx->use_copy_stream = atoi(env) != 0;
-  if (const char* env = getenv("JXLB200_ANS_WARPS")) { const int v = atoi(env); if (v == 16 || v == 32) ctx->ans_warps = v; }
+  if (const char* env = getenv("JXLB200_ANS_WARPS_SINGLE")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16) ctx->ans_warps_single = v; }
+  if (const char* env = getenv("JXLB200_ANS_WARPS")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16) ctx->ans_warps = v; }
   if (const char* env = getenv("JXLB200_ANS_GPW")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->ans_gpw = v; }
   std::string e;
   if (!ctx->enc.Init(device, &e)) { delete ctx; return nullptr; }
@@ -98,6 +100,7 @@ int jxlb200_encode_device(jxlb200_ctx* ctx, const uint8_t* d_pixels, uint32_t wi
   std::string e;
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
   ctx->enc.set_ans_groups_per_warp(1);
+  ctx->enc.set_ans_warps(ctx->ans_warps_single);
   if (!ctx->enc.EncodeDevice(d_pixels, (int)width, (int)height, stride, ep, stats, &e)) return fail(ctx, e);
   return 0;
 }
@@ -120,6 +123,7 @@ int jxlb200_encode(jxlb200_ctx* ctx, const jxlb200_image* image, const jxlb200_p
   std::string e;
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
   ctx->enc.set_ans_groups_per_warp(1);
+  ctx->enc.set_ans_warps(ctx->ans_warps_single);
   ctx->enc.set_copy_stream(nullptr);
   if (!ctx->enc.EncodeHost(image->pixels, (int)image->width, (int)image->height, image->stride, ep, stats, &e))
     return fail(ctx, e);
@@ -158,7 +162,7 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
-    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : 16);
+    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : ctx->ans_warps_single);
     ctx->pipe(p)->set_copy_stream(P > 1 && ctx->use_copy_stream ? ctx->copy_stream : nullptr);
     if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
       rc = fail(ctx, e);
@@ -207,7 +211,7 @@ int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels
     if (rc) break;
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
-    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : 16);
+    ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : ctx->ans_warps_single);
     const auto tq0 = std::chrono::steady_clock::now();
     if (!ctx->pipe(p)->EnqueueDevice(d_pixels[i], (int)widths[i], (int)heights[i], strides[i], ep, &e)) { rc = fail(ctx, e); break; }
     enqueue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();

@@ -53,7 +53,7 @@ class Encoder {
   bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
   bool in_flight_ = false;
   int dct8_variant_ = 4, dct8_rows_ = 2, dct8_tps_ = 512;   // DCT8 kernel: 4 = two threads per block (default), 1 = 8 lanes per block
-  int ans_groups_per_warp_ = 1, ans_warps_ = 16;
+  int ans_groups_per_warp_ = 1, ans_warps_ = 8;
   unsigned launches_ = 0;
 
   int device_ = -1;

@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   AnsSymInfo* s_info = reinterpret_cast<AnsSymInfo*>(smem + (size_t)K * kAnsTabSize * 2);  // [K][64]
   uint8_t* s_cmap = reinterpret_cast<uint8_t*>(s_info + (size_t)K * kAcAlphabet);          // [7425 -> 7440]
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_cmap + 7440);                          // [warps][34]
+  uint2* s_ops = reinterpret_cast<uint2*>(s_stage + kAnsWarps * kStageWords);                // [warps][2][32]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   {
     const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
@@ -495,14 +496,13 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t state = kAnsInitState;
   long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
   uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
-  int m = n > 0 ? ((n - 1) & 31) + 1 : 0;                  // the first chunk (stream tail) is the partial one
-  uint32_t next_tok = (n - 1 - lane) >= 0 && lane < m ? tk[n - 1 - lane] : 0;
-  for (int hi = n; hi > 0; hi -= m, m = 32) {
-    const int i = hi - 1 - lane;  // lane 0 owns the LAST token of the chunk
-    // per-token chain operands: freq | (shared byte address of the symbol's reverse-map run) << 13, reciprocal
-    uint32_t packed = 4096u, rcp = 0x00100000u, nb = 0, bits = 0;
-    if (lane < m) {
-      const uint32_t tkn = next_tok;
+  uint2* ops = s_ops + warp * 64;                          // two slots of 32 per-token chain operands (packed, rcp)
+
+  // per-token operands of the chain: freq | (shared byte address of the symbol's reverse-map run) << 13, reciprocal;
+  // and the token's extra bits
+  auto prep = [&](uint32_t tkn, bool valid, uint32_t& packed, uint32_t& rcp, uint32_t& nb, uint32_t& bits) {
+    packed = 4096u; rcp = 0x00100000u; nb = 0; bits = 0;
+    if (valid) {
       const uint32_t cl = s_cmap[tkn >> 16];
       uint32_t tok;
       hybrid_encode(tkn & 0xFFFF, tok, nb, bits);
@@ -510,84 +510,129 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
       packed = si.freq | ((rmap_saddr + 2u * (cl * kAnsTabSize + si.base)) << 13);
       rcp = si.rcp;
     }
-    { const int in = hi - m - 1 - lane; next_tok = in >= 0 ? tk[in] : 0; }   // prefetch the next (full) chunk
-    uint32_t my_o16 = 0; int my_emit = 0;
-    if (m == 32) {
-      // full chunk: broadcast all operands first (64 independent shuffles, pipelined), then run the
-      // 32-step chain on registers only: ISETP -> SEL -> IMAD.HI -> IMAD -> SEL -> LDS -> IMAD
-      uint32_t pf[32], prc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        pf[j] = __shfl_sync(0xffffffffu, packed, j); prc[j] = __shfl_sync(0xffffffffu, rcp, j);
-        // volatile: keeps all 64 shuffles ahead of the (volatile) loads of the chain, i.e. off its critical path
-        asm volatile("" : "+r"(pf[j]), "+r"(prc[j]));
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t f = pf[j] & 0x1FFF, tab_a = pf[j] >> 13;
-        uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;   // all off the state chain
-        // opaque to the optimiser, so that it keeps r = q * negf + x2 and the two parallel address forms
-        // instead of re-deriving them from f on the serial chain
-        asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
-        const bool emit = state > thr;
-        if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
-        const uint32_t x2 = emit ? (state >> 16) : state;
-        const uint32_t q = __umulhi(x2, prc[j]);
-        const uint32_t r = q * negf + x2;
-        const bool fix = r >= f;
-        const uint32_t a_lo = tab_a + 2 * r, a_hi = tab_b + 2 * r;
-        uint16_t v;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
-        state = ((fix ? q + 1 : q) << kAnsLogTabSize) + v;
-      }
-    } else {
-      for (int j = 0; j < m; ++j) {
-        const uint32_t pk = __shfl_sync(0xffffffffu, packed, j);
-        const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
-        const uint32_t f = pk & 0x1FFF, tab = pk >> 13;
-        const bool emit = (state >> (32 - kAnsLogTabSize)) >= f;
-        if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
-        if (emit) state >>= 16;
-        uint32_t q = __umulhi(state, rc);
-        uint32_t r = state - q * f;
-        if (r >= f) { ++q; r -= f; }
-        uint16_t v;
-        asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(tab + 2 * r));
-        state = (q << kAnsLogTabSize) + v;
-      }
-    }
-    // ---- place the chunk's pieces: lane j's piece = [renorm word (16)][extra bits (nb)], earlier lanes later in the stream
-    const int len = (lane < m) ? (int)nb + (my_emit ? 16 : 0) : 0;
-    const uint32_t val = my_emit ? (my_o16 | (bits << 16)) : bits;
-    int incl = len;
+  };
+  // one chain step on operands (pk, rc); lane j records what step j pushed out
+  auto step = [&](uint32_t pk, uint32_t rc, int j, uint32_t& my_o16, int& my_emit) {
+    const uint32_t f = pk & 0x1FFF, tab_a = pk >> 13;
+    uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;   // all off the state chain
+    asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
+    const bool emit = state > thr;
+    if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
+    const uint32_t x2 = emit ? (state >> 16) : state;
+    const uint32_t q = __umulhi(x2, rc);
+    const uint32_t r = q * negf + x2;
+    const bool fix = r >= f;
+    const uint32_t a_lo = tab_a + 2 * r, a_hi = tab_b + 2 * r;
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
+    state = ((fix ? q + 1 : q) << kAnsLogTabSize) + v;
+  };
+  // Placing a chunk's pieces (lane j's piece = [renorm word (16)][extra bits (nb)], earlier lanes later in the
+  // stream) in three phases separated by warp barriers, so that the chain of the NEXT chunk can run between them.
+  struct PackState { int len, incl, nwords, first_final; uint32_t val; long long lo_bit, base_word; };
+  auto pack_a = [&](uint32_t nb, uint32_t bits, uint32_t o16, int emit, bool valid, PackState& P) {
+    P.len = valid ? (int)nb + (emit ? 16 : 0) : 0;
+    P.val = emit ? (o16 | (bits << 16)) : bits;
+    int incl = P.len;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    P.incl = incl;
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    const long long lo_bit = end_bit - total;                 // first stream bit of this chunk
-    const long long base_word = lo_bit >> 5;                  // lowest word touched
+    P.lo_bit = end_bit - total;                               // first stream bit of this chunk
+    P.base_word = P.lo_bit >> 5;                              // lowest word touched
     const long long top_word = end_bit >> 5;                  // word holding `carry` (if end_bit is unaligned)
-    const int nwords = (int)(((end_bit + 31) >> 5) - base_word);  // words covering [lo_bit, end_bit): <= 31
-    stage[lane] = 0;
-    if (lane < 2) stage[32 + lane] = 0;
-    __syncwarp();
-    if (lane == 0 && (end_bit & 31)) stage[top_word - base_word] = carry;
-    __syncwarp();
-    if (len) {
-      const long long p = end_bit - incl;                     // stream position of my piece
-      const int off = (int)(p - (base_word << 5));
-      const unsigned long long v = (unsigned long long)val << (off & 31);
+    P.nwords = (int)(((end_bit + 31) >> 5) - P.base_word);    // words covering [lo_bit, end_bit): <= 31
+    stage[lane] = (lane == (int)(top_word - P.base_word) && (end_bit & 31)) ? carry : 0;
+    if (lane < 2) stage[32 + lane] = (32 + lane == (int)(top_word - P.base_word) && (end_bit & 31)) ? carry : 0;
+  };
+  auto pack_b = [&](const PackState& P) {
+    if (P.len) {
+      const long long p = end_bit - P.incl;                   // stream position of my piece
+      const int off = (int)(p - (P.base_word << 5));
+      const unsigned long long v = (unsigned long long)P.val << (off & 31);
       atomicOr(&stage[off >> 5], (uint32_t)v);
-      if ((off & 31) + len > 32) atomicOr(&stage[(off >> 5) + 1], (uint32_t)(v >> 32));
+      if ((off & 31) + P.len > 32) atomicOr(&stage[(off >> 5) + 1], (uint32_t)(v >> 32));
     }
-    __syncwarp();
+  };
+  auto pack_c = [&](const PackState& P) {
     // words strictly above the (possibly partial) lowest word are final
-    const int first_final = (lo_bit & 31) ? 1 : 0;
-    for (int w = first_final + lane; w < nwords; w += 32) {
-      if (base_word + w < (long long)kTokensPerGroupMax) out[base_word + w] = stage[w];
+    const int first_final = (P.lo_bit & 31) ? 1 : 0;
+    for (int w = first_final + lane; w < P.nwords; w += 32) {
+      if (P.base_word + w < (long long)kTokensPerGroupMax) out[P.base_word + w] = stage[w];
     }
     carry = stage[0];
+    end_bit = P.lo_bit;
+  };
+
+  // ---- the stream tail: the (possibly partial) last chunk of tokens, not pipelined
+  const int m0 = n > 0 ? ((n - 1) & 31) + 1 : 0;
+  uint32_t nb_p = 0, bits_p = 0, o16_p = 0; int emit_p = 0;   // pieces of the chunk whose chain has run, not yet placed
+  bool valid_p = false;
+  if (n > 0) {
+    uint32_t packed, rcp;
+    const uint32_t tkn = lane < m0 ? tk[n - 1 - lane] : 0;
+    prep(tkn, lane < m0, packed, rcp, nb_p, bits_p);
+    for (int j = 0; j < m0; ++j) {
+      const uint32_t pk = __shfl_sync(0xffffffffu, packed, j);
+      const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
+      step(pk, rc, j, o16_p, emit_p);
+    }
+    valid_p = lane < m0;
+  }
+  // ---- full chunks, software-pipelined: while the serial chain of chunk c runs (a dependent sequence that leaves
+  // most issue slots empty), the same warp prepares the operands of chunk c + 1 and places the pieces of chunk c - 1
+  const int full = n > 0 ? (n - m0) >> 5 : 0;
+  uint32_t nb_c = 0, bits_c = 0;
+  if (full > 0) {
+    uint32_t packed, rcp;
+    prep(tk[n - m0 - 1 - lane], true, packed, rcp, nb_c, bits_c);
+    ops[lane] = make_uint2(packed, rcp);
+  }
+  uint32_t tok_next = full > 1 ? tk[n - m0 - 32 - 1 - lane] : 0;
+  for (int c = 0; c < full; ++c) {
+    const uint2* cur = ops + (c & 1) * 32;
+    uint2* nxt = ops + ((c + 1) & 1) * 32;
+    __syncwarp();   // operands of chunk c visible; stage free
+    uint32_t o16_c = 0; int emit_c = 0;
+    PackState P;
+    // (a) first quarter of the chain || operands of the next chunk
+    uint32_t nb_n = 0, bits_n = 0;
+    {
+      uint32_t packed, rcp;
+      prep(tok_next, c + 1 < full, packed, rcp, nb_n, bits_n);
+      nxt[lane] = make_uint2(packed, rcp);
+      const int in = n - m0 - 32 * (c + 2) - 1 - lane;
+      tok_next = (c + 2 < full) ? tk[in] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    // (b) second quarter || prefix sum of the previous chunk's piece lengths, staging window cleared
+    pack_a(nb_p, bits_p, o16_p, emit_p, valid_p, P);
+#pragma unroll
+    for (int j = 8; j < 16; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
     __syncwarp();
-    end_bit = lo_bit;
+    // (c) third quarter || the previous chunk's pieces OR-ed into the window
+    pack_b(P);
+#pragma unroll
+    for (int j = 16; j < 24; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    __syncwarp();
+    // (d) last quarter || finished words stored
+    pack_c(P);
+#pragma unroll
+    for (int j = 24; j < 32; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    nb_p = nb_c; bits_p = bits_c; o16_p = o16_c; emit_p = emit_c; valid_p = true;
+    nb_c = nb_n; bits_c = bits_n;
+  }
+  // ---- drain: the pieces of the last chunk whose chain has run
+  if (n > 0) {
+    PackState P;
+    __syncwarp();
+    pack_a(nb_p, bits_p, o16_p, emit_p, valid_p, P);
+    __syncwarp();
+    pack_b(P);
+    __syncwarp();
+    pack_c(P);
+    __syncwarp();
   }
   // final state (32 bits) in front, then flush the partial word
   {
@@ -646,7 +691,7 @@ static void launch_ans_groups_w(const uint32_t* tokens, const uint32_t* token_co
                                 const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
                                 uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
   const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
-                      kAnsWarps * kStageWords * 4;
+                      kAnsWarps * kStageWords * 4 + kAnsWarps * 64 * sizeof(uint2);
   cudaFuncSetAttribute(k_ans_groups<kAnsWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int per_cta = kAnsWarps * (groups_per_warp < 1 ? 1 : groups_per_warp);
   cudaMemsetAsync(work_counter, 0, 4, s);
@@ -654,18 +699,22 @@ static void launch_ans_groups_w(const uint32_t* tokens, const uint32_t* token_co
       tokens, token_counts, cmap, (const AnsSymInfo*)info, rmap, num_clusters, num_groups, work_counter, out_arena, start_bit);
 }
 
-// warps_per_cta: 16 for a single image (lowest latency: the chains spread over more SMs), 32 in batch mode (a CTA holds
-// the whole SM's shared memory for its reverse maps, so twice the chains per CTA halves the SM time of the stage)
+// warps_per_cta: 8 for a single image (135 chains of a 4K frame spread over 17 SMs, two warps per scheduler: a chain
+// issues ~25 % of the cycles, so four of them on one scheduler slow each other down), 16 in batch mode (a CTA holds the
+// whole SM's shared memory for its reverse maps: more chains per CTA = less SM time taken from the other pipelines)
 void launch_ans_groups(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
                        const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
                        int warps_per_cta, uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
   ++g_kernel_launches;
-  if (warps_per_cta >= 32)
-    launch_ans_groups_w<32>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
-                            start_bit, num_groups, s);
-  else
+  if (warps_per_cta >= 16)
     launch_ans_groups_w<16>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
                             start_bit, num_groups, s);
+  else if (warps_per_cta >= 8)
+    launch_ans_groups_w<8>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
+                           start_bit, num_groups, s);
+  else
+    launch_ans_groups_w<4>(tokens, token_counts, cmap, info, rmap, num_clusters, work_counter, groups_per_warp, out_arena,
+                           start_bit, num_groups, s);
 }
 
 int cluster_num_clusters_offset() { return (int)offsetof(ClusterState, num_clusters); }

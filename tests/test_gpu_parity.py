@@ -48,6 +48,18 @@ def test_stage_parity_dct8(pkg, oracle, encoder, w, h, flags):
     compare_all(pkg, oracle, encoder, img, 1.0, 7, 3, flags, FLOAT_STAGES + INT_STAGES + ("coeffs",))
 
 
+def test_stage_parity_very_small_distance(pkg, oracle, encoder):
+    """distance 0.02 on hard edges: quantised values beyond the DCT8 kernel's 1024-entry dequantisation-bias table
+    (its formula path) and quants at the 255 / 256 clamps."""
+    rng = np.random.default_rng(5)
+    img = pkg.synth_image(264, 136, 9)
+    img[::3, ::5] = 255
+    img[40:80, 100:160] = rng.integers(0, 2, (40, 60, 3), dtype=np.uint8) * 255
+    for d in (0.02, 0.1):
+        compare_all(pkg, oracle, encoder, img, d, 7, 0, 1, INT_STAGES + ("coeffs",))
+        assert np.abs(encoder.dump("coeffs").astype(np.int32)).max() >= 1024 or d > 0.02
+
+
 @pytest.mark.parametrize("distance", [0.5, 1.0, 1.5, 3.0, 8.0, 14.0])
 def test_stage_parity_distances(pkg, oracle, encoder, distance):
     img = pkg.synth_image(320, 256, 11)
@@ -271,7 +283,8 @@ def test_full_size_search_codestream_equals_oracle(pkg, oracle, encoder):
     assert sum(1 for c in st.acs_histogram if c) >= 6
 
 
-@pytest.mark.parametrize("w,h,proposal,flags", [(256, 200, 3, 0), (512, 384, 0, 1), (131, 77, 1, 0), (640, 480, 2, 0)])
+@pytest.mark.parametrize("w,h,proposal,flags", [(256, 200, 3, 0), (512, 384, 0, 1), (131, 77, 1, 0), (640, 480, 2, 0), (8, 8, 3, 0),
+                                                (1, 1, 0, 1), (257, 9, 3, 0)])
 def test_quality_stats_equal_oracle(pkg, oracle, encoder, w, h, proposal, flags):
     """FLAG_QUALITY: the device reconstructs the frame it coded (dequantise, DC -> LLF, chroma-from-luma, inverse
     transforms of every strategy, XYB -> 8-bit sRGB) and returns the per-channel squared error against the input:
@@ -285,7 +298,7 @@ def test_quality_stats_equal_oracle(pkg, oracle, encoder, w, h, proposal, flags)
         f.close()
         assert st.sse == want, (distance, st.sse, want)
         mse = sum(want) / (3.0 * w * h)
-        assert abs(st.psnr - 10.0 * np.log10(255.0 ** 2 / mse)) < 1e-9
+        assert (np.isinf(st.psnr) and st.psnr > 0) if mse == 0 else abs(st.psnr - 10.0 * np.log10(255.0 ** 2 / mse)) < 1e-9
         # the codestream does not depend on the flag
         data0, st0 = encoder.encode(img, distance, 7, proposal, flags)
         assert data0 == data and st0.sse is None

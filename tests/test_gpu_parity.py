@@ -314,3 +314,12 @@ def test_quality_stats_batch_and_full_size(pkg, oracle, encoder):
     datas, sts = encoder.encode_batch(imgs, 1.0, 7, 0, pkg.FLAG_FIXED_DCT8 | pkg.FLAG_QUALITY)
     for a, b in zip(single, sts):
         assert a.sse == b.sse and a.psnr == b.psnr and 30.0 < a.psnr < 60.0
+
+
+def test_randomised_parity_sweep():
+    """60 random (size, content, distance, effort, proposal, flags) cases: codestream and quality statistics equal the
+    oracle's (tools/stress_parity.py runs the same sweep at any length; 3 300 cases were clean in round 1)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "60", "11"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

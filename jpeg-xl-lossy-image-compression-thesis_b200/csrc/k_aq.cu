@@ -13,6 +13,9 @@
 #include "jxl_common.cuh"
 #include "kernels.h"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace jxlb {
 
 __device__ __forceinline__ float ratio_cbrt_to_gamma(float v, bool invert) {
@@ -213,31 +216,46 @@ __global__ void k_fill(float* p, size_t n, float v) {
 }
 
 // ---- exact k-th smallest by 3-pass radix selection on positive-float bit patterns --------
-// single CTA (the field has one float per 8x8 block: 130k values for a 4K frame)
+// ONE THREAD-BLOCK CLUSTER of 8 CTAs (the field has one float per 8x8 block: 130k values for a 4K frame; a single CTA
+// spent 207 us on the six passes).  Every CTA histograms one eighth of the values into its own shared memory; the bins
+// are then summed slice-wise through distributed shared memory (CTA r owns bins [r * nb/8, (r+1) * nb/8) of all eight
+// histograms), the slice sums are exchanged the same way, and the CTA whose slice holds the k-th element scans it and
+// writes the selected digit into every CTA's shared memory.  Three cluster barriers per pass, no global scratch.
+constexpr int kQpCtas = 8;
+constexpr int kQpThreads = 1024;
+
+struct SelectShared {
+  uint32_t hist[4096];
+  uint32_t tot[4096 / kQpCtas];
+  uint32_t slice_sum[kQpCtas];
+  uint32_t prefix, k;
+};
+
 template <bool kDeviation>
-__device__ uint32_t radix_select(const float* __restrict__ v, size_t n, size_t k, float center, uint32_t* hist /*4096*/,
-                                 uint32_t* sh_prefix, uint32_t* sh_k) {
+__device__ uint32_t radix_select(cg::cluster_group& cluster, const float* __restrict__ v, size_t n, size_t k, float center,
+                                 SelectShared& sh) {
+  const int rank = (int)cluster.block_rank(), t = threadIdx.x, lane = t & 31;
   uint32_t prefix = 0;  // selected high bits so far
   uint32_t kk = (uint32_t)k;
   const int shifts[3] = {20, 8, 0};
   const int bits[3] = {12, 12, 8};
   int done_bits = 0;
   for (int pass = 0; pass < 3; ++pass) {
-    const int nb = 1 << bits[pass];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
+    const int nb = 1 << bits[pass], per = nb / kQpCtas;
+    for (int i = t; i < nb; i += kQpThreads) sh.hist[i] = 0;
     __syncthreads();
     // the field is narrow-ranged, so most values share a digit: aggregate equal digits inside the
     // warp (match.any) and let one lane per distinct digit do the shared-memory atomic
-    for (size_t i0 = 0; i0 < n; i0 += (size_t)blockDim.x * 8) {
+    for (size_t i0 = (size_t)rank * kQpThreads * 8; i0 < n; i0 += (size_t)kQpCtas * kQpThreads * 8) {
       float vals[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {       // eight independent loads in flight before any of them is consumed
-        const size_t i = i0 + (size_t)u * blockDim.x + threadIdx.x;
+        const size_t i = i0 + (size_t)u * kQpThreads + t;
         vals[u] = i < n ? v[i] : 0.0f;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const size_t i = i0 + (size_t)u * blockDim.x + threadIdx.x;
+        const size_t i = i0 + (size_t)u * kQpThreads + t;
         bool match = false;
         uint32_t digit = 0;
         if (i < n) {
@@ -249,42 +267,66 @@ __device__ uint32_t radix_select(const float* __restrict__ v, size_t n, size_t k
         const unsigned part = __ballot_sync(0xffffffffu, match);
         if (match) {
           const unsigned peers = __match_any_sync(part, digit);
-          if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+          if (lane == (__ffs(peers) - 1)) atomicAdd(&sh.hist[digit], (uint32_t)__popc(peers));
         }
       }
     }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      // warp 0: each lane sums a contiguous run of nb/32 bins, warp scan picks the run, the owning lane the bin
-      const int per = nb / 32, lane = threadIdx.x;
-      uint32_t run = 0;
-      for (int b = lane * per; b < (lane + 1) * per; ++b) run += hist[b];
-      uint32_t incl = run;
+    cluster.sync();
+    // my slice of the bins, summed over the eight histograms
+    if (t < per) {
+      uint32_t sum = 0;
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-      const uint32_t excl = incl - run;
-      if (excl <= kk && kk < incl) {
-        uint32_t acc = excl; int b = lane * per;
-        for (; b < (lane + 1) * per; ++b) { if (acc + hist[b] > kk) break; acc += hist[b]; }
-        *sh_k = kk - acc;
-        *sh_prefix = prefix | ((uint32_t)b << shifts[pass]);
-      }
+      for (int r = 0; r < kQpCtas; ++r) sum += cluster.map_shared_rank(sh.hist, r)[rank * per + t];
+      sh.tot[t] = sum;
     }
     __syncthreads();
-    kk = *sh_k; prefix = *sh_prefix;
+    if (t < 32) {
+      uint32_t run = 0;
+      for (int b = lane; b < per; b += 32) run += sh.tot[b];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) run += __shfl_xor_sync(0xffffffffu, run, d);
+      if (lane < kQpCtas) cluster.map_shared_rank(sh.slice_sum, lane)[rank] = run;
+    }
+    cluster.sync();
+    if (t < 32) {
+      uint32_t excl = 0;
+      for (int r = 0; r < rank; ++r) excl += sh.slice_sum[r];
+      if (excl <= kk && kk < excl + sh.slice_sum[rank]) {
+        // this CTA's slice holds the k-th element: each lane sums a contiguous run of per/32 bins (one bin per lane in the
+        // 8-bit pass), a warp scan picks the run, the owning lane the bin
+        const int run_len = per >= 32 ? per / 32 : 1;
+        uint32_t run = 0;
+        if (lane < per) for (int b = lane * run_len; b < (lane + 1) * run_len; ++b) run += sh.tot[b];
+        uint32_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        const uint32_t lo = excl + incl - run;
+        if (lane < per && lo <= kk && kk < lo + run) {
+          uint32_t acc = lo; int b = lane * run_len;
+          for (; b < (lane + 1) * run_len; ++b) { if (acc + sh.tot[b] > kk) break; acc += sh.tot[b]; }
+          const uint32_t new_k = kk - acc, new_prefix = prefix | ((uint32_t)(rank * per + b) << shifts[pass]);
+          for (int r = 0; r < kQpCtas; ++r) {
+            SelectShared* rs = cluster.map_shared_rank(&sh, r);
+            rs->k = new_k; rs->prefix = new_prefix;
+          }
+        }
+      }
+    }
+    cluster.sync();
+    kk = sh.k; prefix = sh.prefix;
     done_bits += bits[pass];
-    __syncthreads();
   }
   return prefix;
 }
 
-__global__ void __launch_bounds__(1024) k_quant_params(const float* __restrict__ qf, size_t n, float quant_dc,
-                                                       QuantDev* __restrict__ q) {
-  __shared__ uint32_t hist[4096];
-  __shared__ uint32_t sh_prefix, sh_k;
-  const float median = __uint_as_float(radix_select<false>(qf, n, n / 2, 0.0f, hist, &sh_prefix, &sh_k));
-  const float mad = __uint_as_float(radix_select<true>(qf, n, n / 2, median, hist, &sh_prefix, &sh_k));
-  if (threadIdx.x == 0) {
+__global__ void __cluster_dims__(kQpCtas, 1, 1) __launch_bounds__(kQpThreads)
+    k_quant_params(const float* __restrict__ qf, size_t n, float quant_dc, QuantDev* __restrict__ q) {
+  __shared__ SelectShared sh;
+  cg::cluster_group cluster = cg::this_cluster();
+  const float median = __uint_as_float(radix_select<false>(cluster, qf, n, n / 2, 0.0f, sh));
+  const float mad = __uint_as_float(radix_select<true>(cluster, qf, n, n / 2, median, sh));
+  cluster.sync();   // nobody leaves while its shared memory can still be addressed by a peer
+  if (cluster.block_rank() == 0 && threadIdx.x == 0) {
     float scale = 65536.0f * (median - mad) / 5.0f;
     if (!(scale >= 1.0f)) scale = 1.0f;
     if (scale > 32768.0f) scale = 32768.0f;
@@ -339,7 +381,7 @@ void launch_fill(float* p, size_t n, float v, cudaStream_t s) {
 
 void launch_quant_params(const float* qf, size_t n, float quant_dc, QuantDev* q, cudaStream_t s) {
   ++g_kernel_launches;
-  k_quant_params<<<1, 1024, 0, s>>>(qf, n, quant_dc, q);
+  k_quant_params<<<kQpCtas, kQpThreads, 0, s>>>(qf, n, quant_dc, q);
 }
 
 void launch_raw_qf(const float* qf, const uint8_t* acs, const FrameDim& fd, const QuantDev* q, const uint8_t* cvx,

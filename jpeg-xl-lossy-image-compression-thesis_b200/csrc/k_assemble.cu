@@ -118,7 +118,7 @@ __device__ void write_size_u32(BitWriterDev& w, uint32_t v) {
   else { w.write(2, 3); w.write(30, m); }
 }
 
-__global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, int b_qm_scale, const uint32_t* __restrict__ lf_bits,
+__global__ void __launch_bounds__(256) k_finalize(FrameDim fd, int x_qm_scale, int b_qm_scale, const uint32_t* __restrict__ lf_bits,
                                                  const uint32_t* __restrict__ dg_start_bit, const uint32_t* __restrict__ mod_total_bits,
                                                  const uint32_t* __restrict__ hf_bits, const unsigned long long* __restrict__ group_start_bit,
                                                  Section* __restrict__ sections, uint32_t* __restrict__ hdr_stage,
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
                                                  unsigned long long* __restrict__ out_info, const QuantDev* __restrict__ qd,
                                                  const uint32_t* __restrict__ token_counts,
                                                  const int* __restrict__ num_clusters_p) {
-  {  // statistics block read back by the host together with the size (one pinned copy)
+  if (threadIdx.x < 32) {  // statistics block read back by the host together with the size (one pinned copy)
     unsigned long long nt = 0;
     for (int g = threadIdx.x; g < fd.num_groups; g += 32) nt += token_counts[g];
 #pragma unroll
@@ -136,12 +136,14 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
       out_info[4] = nt; out_info[5] = (unsigned long long)*num_clusters_p;
     }
   }
-  if (threadIdx.x != 0) return;
+  // section sources and lengths: one thread per section (a serial loop paid one global-load round trip per section);
+  // the lengths stay in shared memory for the TOC and the placement below
+  extern __shared__ unsigned long long s_nbits[];   // [nsec] lengths, then [nsec] destination bits
   const int ndc = fd.num_dc_groups, ng = fd.num_groups;
   const bool small = ng == 1;
   const int nsec = 2 + ndc + ng;
-  // section sources and lengths
-  for (int i = 0; i < nsec; ++i) {
+  unsigned long long* s_dst = s_nbits + nsec;
+  for (int i = threadIdx.x; i < nsec; i += blockDim.x) {
     Section s;
     if (i == 0) { s.kind = 0; s.index = 0; s.src_bit = 0; s.nbits = *lf_bits; }
     else if (i <= ndc) {
@@ -155,7 +157,13 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
     }
     s.dst_bit = 0;
     sections[i] = s;
+    s_nbits[i] = s.nbits;
   }
+  __syncthreads();
+  __shared__ unsigned long long s_pos;
+  __shared__ uint32_t s_header_bits;
+  __shared__ int s_overflow;
+  if (threadIdx.x == 0) {
   // codestream headers, frame header and TOC into the staging words
   BitWriterDev w;
   w.init(hdr_stage);
@@ -177,10 +185,10 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
   w.write(1, 0);                                  // TOC not permuted
   if (w.bits() & 7) w.write(8 - (int)(w.bits() & 7), 0);
   unsigned long long total_small_bits = 0;
-  if (small) for (int i = 0; i < nsec; ++i) total_small_bits += sections[i].nbits;
+  if (small) for (int i = 0; i < nsec; ++i) total_small_bits += s_nbits[i];
   const int ntoc = small ? 1 : nsec;
   for (int i = 0; i < ntoc; ++i) {
-    const uint32_t size = (uint32_t)(((small ? total_small_bits : sections[i].nbits) + 7) >> 3);
+    const uint32_t size = (uint32_t)(((small ? total_small_bits : s_nbits[i]) + 7) >> 3);
     if (size < 1024) { w.write(2, 0); w.write(10, size); }
     else if (size < 17408) { w.write(2, 1); w.write(14, size - 1024); }
     else if (size < 4211712) { w.write(2, 2); w.write(22, size - 17408); }
@@ -191,22 +199,27 @@ __global__ void __launch_bounds__(32) k_finalize(FrameDim fd, int x_qm_scale, in
   const uint32_t header_bits = w.bits();
   unsigned long long pos = header_bits;
   for (int i = 0; i < nsec; ++i) {
-    sections[i].dst_bit = pos;
-    pos += small ? sections[i].nbits : ((sections[i].nbits + 7) & ~7ull);
+    s_dst[i] = pos;
+    pos += small ? s_nbits[i] : ((s_nbits[i] + 7) & ~7ull);
   }
   pos = (pos + 7) & ~7ull;
   const bool overflow = pos + 64 > out_capacity_bits;
   out_info[0] = overflow ? 0 : pos >> 3;
   out_info[1] = overflow ? 1 : 0;
-  if (overflow) return;
+  s_pos = pos; s_header_bits = header_bits; s_overflow = overflow ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_overflow) return;
   // the words a section covers only partially are ORed into by k_assemble: clear them first
-  for (int i = 0; i < nsec; ++i) {
-    const unsigned long long a = sections[i].dst_bit, b = a + sections[i].nbits;
+  for (int i = threadIdx.x; i < nsec; i += blockDim.x) {
+    const unsigned long long a = s_dst[i], b = a + s_nbits[i];
+    sections[i].dst_bit = a;
     out_words[a >> 5] = 0;
     out_words[b >> 5] = 0;
   }
-  out_words[pos >> 5] = 0;
-  for (uint32_t i = 0; i < (header_bits + 31) / 32; ++i) out_words[i] = hdr_stage[i];
+  if (threadIdx.x == 0) out_words[s_pos >> 5] = 0;
+  __syncthreads();   // (the header words below overlap the first section's first word)
+  for (uint32_t i = threadIdx.x; i < (s_header_bits + 31) / 32; i += blockDim.x) out_words[i] = hdr_stage[i];
 }
 
 __global__ void __launch_bounds__(256) k_assemble(const Section* __restrict__ sections, const uint32_t* __restrict__ lf_words,
@@ -247,7 +260,9 @@ void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const u
                      unsigned long long* out_info, const QuantDev* qd, const uint32_t* token_counts, const int* num_clusters,
                      cudaStream_t s) {
   ++g_kernel_launches;
-  k_finalize<<<1, 32, 0, s>>>(fd, x_qm_scale, b_qm_scale, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
+  const size_t smem = (size_t)2 * (2 + fd.num_dc_groups + fd.num_groups) * sizeof(unsigned long long);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_finalize<<<1, 256, smem, s>>>(fd, x_qm_scale, b_qm_scale, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
                              sections, hdr_stage, out_words, out_capacity_bits, out_info, qd, token_counts, num_clusters);
 }
 

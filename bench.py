@@ -43,7 +43,7 @@ WORKLOADS = {
 STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
 # DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), per workload kernel;
 # filled from profiles/ (None = not captured for this kernel)
-TRAFFIC_BYTES = {"coeff": 121.1e6}   # profiles/r01e_dct8_v4_full.txt: 100.1 MB read + 21.0 MB written (k_dct8_quant_v4)
+TRAFFIC_BYTES = {"coeff": 120.4e6}   # profiles/r01f_dct8_v4_recon_full.txt: 100.1 MB read + 20.3 MB written (k_dct8_quant_v4<2, 512>)
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (64: 22.2 GP/s, 256: 25.6 GP/s — the "
+    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (64: ~24 GP/s, 256: ~28 GP/s — the "
                     "pipeline's fill and drain, ~4 ms of rANS latency per image, amortise over the step)")
     ap.add_argument("--pipelines", type=int, default=32, help="images in flight per rank (CUDA streams)")
     args = ap.parse_args()
@@ -316,6 +316,8 @@ def main():
         achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
         per_stage = {}
         for sname, bpp_alg in STAGE_BYTES_PER_PX.items():
+            if sname == "homog" and proposal == 0:
+                continue                                    # the map is only computed for the proposals (a memset otherwise)
             t_ms = float(mean_stage[STAGE_INDEX[sname]])
             per_stage[sname] = {"ms": t_ms, "GB/s": bpp_alg * w * h / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0,
                                 "frac": (bpp_alg * w * h / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else 0.0}
@@ -330,8 +332,9 @@ def main():
                                   "ms": float(mean_stage[STAGE_INDEX["ans"]]), "tokens": int(last_stats.num_tokens),
                                   "Mtokens_per_s": (last_stats.num_tokens / 1e6) / (float(mean_stage[STAGE_INDEX["ans"]]) / 1e3)
                                   if mean_stage[STAGE_INDEX["ans"]] > 0 else 0.0,
-                                  "bound": "dependency latency of the longest group's chain (~126 cycles per token, ncu: "
-                                           "fixed-latency waits 49 %, shared-memory loads 22 %, issue 23 %), not bandwidth"},
+                                  "bound": "dependency latency of the longest group's chain (~115 cycles per token after "
+                                           "software pipelining; ncu profiles/r01h: fixed-latency waits 42 %, shared-memory "
+                                           "loads 19 %, issue 23 %), not bandwidth"},
                 "note": "per-kernel times from single-image encodes (one stream); the largest stage, the per-group "
                         "rANS chains (ans), is serial-latency bound, not bandwidth bound: see profiles/"}
         line = {

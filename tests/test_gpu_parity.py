@@ -302,6 +302,12 @@ def test_quality_stats_equal_oracle(pkg, oracle, encoder, w, h, proposal, flags)
         # the codestream does not depend on the flag
         data0, st0 = encoder.encode(img, distance, 7, proposal, flags)
         assert data0 == data and st0.sse is None
+        # and the statistics describe what the BITSTREAM carries: decoding the bytes with the independent self-decoder
+        # (entropy decode, dequantise, inverse transforms, colour) gives the same squared error
+        rec = oracle.decode_pixels(data, w, h)
+        assert rec is not None
+        d2 = (rec.astype(np.int64) - img.astype(np.int64)) ** 2
+        assert [int(d2[:, :, c].sum()) for c in range(3)] == st.sse
 
 
 def test_quality_stats_batch_and_full_size(pkg, oracle, encoder):

@@ -537,11 +537,8 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
                           const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
                           uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_coeff_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoeffShared));
-    configured = true;
-  }
+  // (function attributes are per device: set on every launch, a context may live on any GPU of the process)
+  cudaFuncSetAttribute(k_coeff_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoeffShared));
   CoeffArgs A;
   A.fd = fd; A.qd = qd; A.T = T;
   for (int i = 0; i < 13; ++i) A.inv_order[i] = inv_order[i];

@@ -658,11 +658,8 @@ size_t cluster_state_bytes() { return sizeof(ClusterState); }
 void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* nzcount, const uint16_t* lastk,
                      const int16_t* coeffs, const FrameDim& fd, uint32_t* tokens, uint32_t* token_counts, uint32_t* hist,
                      cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNumAcContexts * sizeof(uint32_t)));
-    configured = true;
-  }
+  // (function attributes are per device: set on every launch, a context may live on any GPU of the process)
+  cudaFuncSetAttribute(k_tokenize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kNumAcContexts * sizeof(uint32_t)));
   ++g_kernel_launches;
   k_tokenize<<<dim3(fd.num_groups, kTokSplit), 256, kNumAcContexts * sizeof(uint32_t), s>>>(acs, nzeros, nzcount, lastk, coeffs, fd, tokens, token_counts, hist);
 }
@@ -670,12 +667,9 @@ void launch_tokenize(const uint8_t* acs, const uint8_t* nzeros, const uint16_t* 
 void launch_cluster(const uint32_t* hist, const int* lut, void* state, uint8_t* cmap, uint32_t* cluster_hist,
                     cudaStream_t s) {
   ++g_kernel_launches;
-  static bool configured = false;
   const size_t smem = (size_t)(kClusterThreads / 32) * kCacheCap * kAcAlphabet * sizeof(uint32_t);
-  if (!configured) {
-    cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  // (function attributes are per device: set on every launch, a context may live on any GPU of the process)
+  cudaFuncSetAttribute(k_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k_cluster<<<kClusterCtas, kClusterThreads, smem, s>>>(hist, lut, (ClusterState*)state, cmap, cluster_hist, kMaxClusters);
 }
 

@@ -329,3 +329,25 @@ def test_randomised_parity_sweep():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "60", "11"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_devices_in_one_process(pkg, oracle):
+    """Contexts on different GPUs of one process (the C ABI allows it: jxlb200_create(device)) give the same bytes;
+    covers per-device state such as kernel attributes and constant tables.  Needs two visible GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    img = pkg.synth_image(520, 264, 77)
+    outs = []
+    for dev in (1, 0, 1):
+        with pkg.Encoder(dev) as enc:
+            for (proposal, flags) in ((3, pkg.FLAG_QUALITY), (0, pkg.FLAG_FIXED_DCT8)):
+                data, st = enc.encode(img, 1.0, 7, proposal, flags)
+                outs.append((dev, proposal, data, st.sse))
+    ref = {}
+    for dev, proposal, data, sse in outs:
+        ref.setdefault(proposal, (data, sse))
+        assert (data, sse) == ref[proposal], (dev, proposal)
+    want = oracle.encode(img, 1.0, 7, 3, 0)
+    assert ref[3][0] == want.dump("codestream").tobytes()
+    want.close()

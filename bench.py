@@ -237,6 +237,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     pkg = importlib.import_module(PKG)
+    # one process per GPU: run on (and allocate the pinned input buffers from) the GPU's own NUMA node
+    numa = pkg.bind_to_gpu_numa_node(local_rank) if os.environ.get("JXLB200_NUMA_BIND", "1") != "0" else {"numa_node": "off"}
     w, h, distance, effort, proposal, flags = WORKLOADS[args.workload]
     mp = w * h / 1e6
     B = args.batch                               # images per rank per step, args.pipelines of them in flight
@@ -346,7 +348,8 @@ def main():
                        "pipelines_per_rank": args.pipelines,
                        "l2": "flushed between timed iterations (256 MiB fill, untimed); distinct inputs per step "
                              f"{n_distinct * 3 * w * h >> 20} MiB",
-                       "parallelism": f"image-sharded x{world}, no data-path collective"},
+                       "parallelism": f"image-sharded x{world}, no data-path collective",
+                       "host_placement": f"rank 0 bound to NUMA node {numa.get('numa_node')} ({numa.get('cpus')} cpus)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * B * 3 * w * h,
                     "d2h_bytes_per_step": world * out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps,

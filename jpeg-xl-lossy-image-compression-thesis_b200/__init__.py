@@ -18,4 +18,6 @@ from .encoder import (  # noqa: F401
     PROPOSAL_COMBINED, FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, STAGES, frame_dims, library_path, load_library,
 )
 from .synth import synth_image, synth_batch  # noqa: F401
-from .sharding import shard_indices, distance_for_image, ShardStats, JobStats, gather_stats  # noqa: F401
+from .sharding import (  # noqa: F401
+    shard_indices, distance_for_image, ShardStats, JobStats, gather_stats, bind_to_gpu_numa_node,
+)

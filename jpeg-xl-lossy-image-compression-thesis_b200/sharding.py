@@ -13,6 +13,34 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pins the calling process to the CPU cores of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated (first touch then places the buffers on that node): with one process per GPU and all ranks' input
+    buffers on one socket, the end-to-end path of an 8-GPU box is limited by the inter-socket link instead of each
+    GPU's own host link.  Best effort: returns what it did ({"numa_node": n, "cpus": k} or {"numa_node": None, ...})."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        pci = torch.cuda.get_device_properties(device_index)
+        bus_id = f"{pci.pci_domain_id:04x}:{pci.pci_bus_id:02x}:{pci.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus_id}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info = {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:   # no sysfs / no permission: keep the default placement
+        info["error"] = repr(e)[:80]
+    return info
+
+
 def shard_indices(num_images: int, rank: int, world: int) -> list[int]:
     """Indices of the images rank ``rank`` encodes: i mod world == rank (round robin, like the reference)."""
     if not (0 <= rank < world):

@@ -3,18 +3,21 @@
 // enc_entropy_coder.cc TokenizeCoefficients, ac_context.h, enc_cluster.cc, enc_ans.cc
 // [UPSTREAM]; algorithmic choices in DESIGN.md "Entropy stage").
 //
-//  k_tokenize    one CTA per 256x256 AC group: token counts per block-channel from
-//                (nzeros, last non-zero scan position), CTA-wide exclusive scan, then one warp per
-//                block-channel emits its tokens with ballot/popc for the running non-zero count;
-//                tokens leave as coalesced 32-bit stores, histogram bins by global REDs.
+//  k_tokenize    four CTAs per 256x256 AC group: token counts per block-channel from (nzeros, last
+//                non-zero scan position), CTA-wide exclusive scan (recomputed by each of the four), then
+//                rounds of 32 block-channel entries drawn from a CTA counter: every lane prefetches one
+//                entry's metadata and first 16 scan positions, the warp walks four entries side by side
+//                (8 lanes each) with ballot/popc for the running non-zero count; tokens leave as 32-bit
+//                stores, histogram bins through shared-memory counters (symbols 0/1) or global REDs.
 //  k_cluster     ONE thread-block cluster of 8 CTAs: farthest-point seeding on an integer
 //                entropy distance; the per-round argmax travels through distributed shared
 //                memory (one cluster barrier per round instead of a grid-wide sync).
 //  k_ans_tables  one warp per cluster histogram: normalise to 4096, code the histogram header,
 //                build the alias table and the encoder's reverse map.
-//  k_ans_groups  one warp per AC group: tokens are fetched 32 at a time (coalesced), their
-//                cluster / symbol info is looked up in parallel, and the serial state chain
-//                runs over warp shuffles; bits are written backwards into the group's arena.
+//  k_ans_groups  one warp per AC group, software-pipelined over chunks of 32 tokens: while the serial state
+//                chain of chunk c runs on operands broadcast from shared memory, the same warp looks up the
+//                cluster / symbol info of chunk c + 1 and places the bits of chunk c - 1 (prefix sum, OR into
+//                a staging window, coalesced stores); the stream grows backwards in the group's arena.
 #include "entropy.cuh"
 #include "kernels.h"
 

@@ -37,6 +37,9 @@ WORKLOADS = {
     "4k_full_d1": (3840, 2160, 1.0, 7, 0, 0),
     "8k_partitioning": (7680, 4320, 1.0, 7, 1, 0),
     "1080p_combined": (1920, 1080, 1.0, 7, 3, 0),
+    # BASELINE configs[4]: 1080p, combined proposal, distance 0.5 .. 3.0 round-robin by GLOBAL image index, image i on
+    # rank i mod N (sharding.distance_for_image / shard_indices); the per-image distance list replaces `distance`
+    "1080p_combined_sweep": (1920, 1080, None, 7, 3, 0),
     "512_d1": (512, 512, 1.0, 7, 0, 0),
 }
 # algorithmic bytes per pixel of each pipeline stage (DESIGN.md "Kernels")
@@ -113,12 +116,13 @@ def cpu_oracle_throughput(workload, budget_images, threads):
     import oracle_lib
     pkg = importlib.import_module(PKG)
     w, h, dist, effort, proposal, flags = WORKLOADS[workload]
+    sweep = dist is None
     ora = oracle_lib.load(rebuild=not os.path.exists(oracle_lib.SO))
     imgs = [pkg.synth_image(w, h, 1000 + i) for i in range(min(budget_images, 2))]
     done = []
 
     def work(k):
-        f = ora.encode(imgs[k % len(imgs)], dist, effort, proposal, flags)
+        f = ora.encode(imgs[k % len(imgs)], pkg.distance_for_image(k) if sweep else dist, effort, proposal, flags)
         assert f.error == "", f.error
         done.append(len(f.dump("codestream")))
         f.close()
@@ -163,7 +167,8 @@ def cjxl_throughput(cjxl, workload, n_images, threads):
             paths.append(path)
         t0 = time.perf_counter()
         for i in range(n_images):
-            subprocess.run([cjxl, paths[i % len(paths)], os.path.join(tmp, "out.jxl"), f"--distance={dist}", f"--effort={effort}",
+            d_i = importlib.import_module(PKG).distance_for_image(i) if dist is None else dist
+            subprocess.run([cjxl, paths[i % len(paths)], os.path.join(tmp, "out.jxl"), f"--distance={d_i}", f"--effort={effort}",
                             f"--num_threads={threads}"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         dt = time.perf_counter() - t0
     return n_images * w * h / 1e6 / dt, dt
@@ -194,7 +199,8 @@ def run_reference(args):
         "impl": "reference", "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "width": w, "height": h, "distance": dist, "effort": effort,
+        "config": {"workload": args.workload, "width": w, "height": h,
+                   "distance": "0.5..3.0 round-robin by global image index" if dist is None else dist, "effort": effort,
                    "proposal": proposal, "flags": flags},
         "cpu_baseline": ({"value": value, "unit": "MP/s", "cores": cores, "kind": "reference",
                           "sample": f"4 images of {w}x{h} per step through {cjxl} --num_threads={cores}"} if cjxl else
@@ -245,6 +251,8 @@ def main():
     n_distinct = min(B, 8)                       # distinct synthetic images per rank (the batch cycles through them)
     imgs = [pkg.synth_image(w, h, rank * 64 + i) for i in range(n_distinct)]
     pinned = [torch.from_numpy(im).pin_memory() for im in imgs]          # e2e inputs: page-locked host memory
+    if distance is None:    # config 5: this rank's images are the global indices rank, rank + world, ...
+        distance = [pkg.distance_for_image(rank + world * i) for i in range(B)]
     h_imgs = [pinned[i % n_distinct].numpy() for i in range(B)]
     d_imgs = [p.cuda() for p in pinned]                                  # value inputs: resident in HBM
     d_ptrs = [d_imgs[i % n_distinct].data_ptr() for i in range(B)]
@@ -284,7 +292,8 @@ def main():
     for i in range(max(3, min(args.steps, 10))):
         flush.fill_(i & 255)
         torch.cuda.synchronize()
-        st1 = enc.encode_device(d_ptrs[i % n_distinct], w, h, 3 * w, distance, effort, proposal, flags)
+        st1 = enc.encode_device(d_ptrs[i % n_distinct], w, h, 3 * w, distance[i % len(distance)] if isinstance(distance, list) else distance,
+                                effort, proposal, flags)
         stage_ms.append(list(st1.stage_ms) + [st1.total_ms])
 
     # ---- e2e: pinned host buffers through jxlb200_encode_batch, wall clock around the calls ----
@@ -343,7 +352,9 @@ def main():
             "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "width": w, "height": h, "distance": distance, "effort": effort,
+            "config": {"workload": args.workload, "width": w, "height": h,
+                       "distance": "0.5..3.0 round-robin by global image index" if isinstance(distance, list) else distance,
+                       "effort": effort,
                        "proposal": proposal, "flags": flags, "images_per_rank_per_step": B,
                        "pipelines_per_rank": args.pipelines,
                        "l2": "flushed between timed iterations (256 MiB fill, untimed); distinct inputs per step "

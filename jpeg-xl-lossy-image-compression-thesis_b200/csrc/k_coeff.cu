@@ -59,11 +59,17 @@ __device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int
   if (gl < H) {
     const int y = gl;
     const int yfix = y >= H / 2 ? 2 : 0;
-#pragma unroll 8
-    for (int x = 0; x < W; ++x) {
+    // (weights are read as 16-byte vectors: rows are 32-byte aligned; a quarter of the global-load instructions)
+#pragma unroll 2
+    for (int x4 = 0; x4 < W; x4 += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(qm + y * W + x4));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+      const int x = x4 + e;
       if (x < xs && y < ys) continue;
       const int hfix = yfix + (x >= W / 2 ? 1 : 0);
-      const float val = coef[y * kTPitch + x] * (qm[y * W + x] * qac * qm_mul);
+      const float val = coef[y * kTPitch + x] * (wv[e] * qac * qm_mul);
       const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
       const float err = fabsf(val - v);
       r_err += err;
@@ -75,6 +81,7 @@ __device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int
         const bool on_border = y == H - 1 || x == W - 1;
         const bool in_larger_corner = x >= 4 * xs && y >= 4 * ys;
         if (in_corner || (on_border && in_larger_corner)) r_hf += fabsf(val);
+      }
       }
     }
   }
@@ -162,15 +169,21 @@ __device__ __forceinline__ void quantize_rows(const float* coef, const float* __
   }
   if (gl < H) {
     const int y = gl, yfix = (y >= H / 2) ? 2 : 0;
-#pragma unroll 8
-    for (int x = 0; x < W; ++x) {
-      const float t = thr[yfix + (x >= W / 2 ? 1 : 0)];
-      const float q = qm[y * W + x] * qac_mul;
-      const float val = q * coef[y * kTPitch + x];
-      int v = (fabsf(val) >= t) ? (int)rintf(val) : 0;
-      if (x < xs && y < ys) v = 0;
-      v = v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
-      out[y * kTPitch + x] = v;
+#pragma unroll 2
+    for (int x4 = 0; x4 < W; x4 += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(qm + y * W + x4));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int x = x4 + e;
+        const float t = thr[yfix + (x >= W / 2 ? 1 : 0)];
+        const float q = wv[e] * qac_mul;
+        const float val = q * coef[y * kTPitch + x];
+        int v = (fabsf(val) >= t) ? (int)rintf(val) : 0;
+        if (x < xs && y < ys) v = 0;
+        v = v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
+        out[y * kTPitch + x] = v;
+      }
     }
   }
 }
@@ -307,11 +320,17 @@ __device__ void process_transform(CoeffShared& sh, int warp, bool active, int ox
   for (int it = 0; it < 3; ++it) {
     const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
     if (it == 1 && gl < H) {
-#pragma unroll 8
-      for (int x = 0; x < W; ++x) {
-        const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dq[size + gl * W + x]) * inv_qac;
-        b0[gl * kTPitch + x] = __fmaf_rn(-x_factor, yrt, b0[gl * kTPitch + x]);
-        b2[gl * kTPitch + x] = __fmaf_rn(-b_factor, yrt, b2[gl * kTPitch + x]);
+#pragma unroll 2
+      for (int x4 = 0; x4 < W; x4 += 4) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dq + size + gl * W + x4));
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int x = x4 + e;
+          const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dv[e]) * inv_qac;
+          b0[gl * kTPitch + x] = __fmaf_rn(-x_factor, yrt, b0[gl * kTPitch + x]);
+          b2[gl * kTPitch + x] = __fmaf_rn(-b_factor, yrt, b2[gl * kTPitch + x]);
+        }
       }
     }
     float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
@@ -327,10 +346,13 @@ __device__ void process_transform(CoeffShared& sh, int warp, bool active, int ox
     const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
     const int* src = reinterpret_cast<const int*>(bufs[c]);
     int nz = 0, last = 0;
+    uint2 inv4 = make_uint2(0u, 0u);
     if (gl < H && active) {
       for (int x = 0; x < W; ++x) {
         const int v = src[gl * kTPitch + x];
-        const int k = inv[gl * W + x];
+        // (scan indices of four positions per 8-byte load)
+        if ((x & 3) == 0) inv4 = __ldg(reinterpret_cast<const uint2*>(inv + gl * W + x));
+        const int k = (int)(((x & 2) ? inv4.y : inv4.x) >> ((x & 1) * 16)) & 0xFFFF;
         const int j = k >> 6;
         const int cbx = bx + (j % cxb), cby = by + (j / cxb);
         const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
@@ -426,10 +448,16 @@ __device__ void process_transform_cp(CoeffShared& sh, int warp, int ox, int oy, 
     const float factor = c == 0 ? 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f
                                 : 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
     if (gl < H) {
-#pragma unroll 8
-      for (int x = 0; x < W; ++x) {
-        const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dq[size + gl * W + x]) * inv_qac;
-        buf[gl * kTPitch + x] = __fmaf_rn(-factor, yrt, buf[gl * kTPitch + x]);
+#pragma unroll 2
+      for (int x4 = 0; x4 < W; x4 += 4) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dq + size + gl * W + x4));
+        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int x = x4 + e;
+          const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dv[e]) * inv_qac;
+          buf[gl * kTPitch + x] = __fmaf_rn(-factor, yrt, buf[gl * kTPitch + x]);
+        }
       }
     }
     float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
@@ -441,10 +469,13 @@ __device__ void process_transform_cp(CoeffShared& sh, int warp, int ox, int oy, 
     const int slot = c == 1 ? 0 : (c == 0 ? 1 : 2);
     const int* src = reinterpret_cast<const int*>(buf);
     int nz = 0, last = 0;
+    uint2 inv4 = make_uint2(0u, 0u);
     if (gl < H) {
       for (int x = 0; x < W; ++x) {
         const int v = src[gl * kTPitch + x];
-        const int k = inv[gl * W + x];
+        // (scan indices of four positions per 8-byte load)
+        if ((x & 3) == 0) inv4 = __ldg(reinterpret_cast<const uint2*>(inv + gl * W + x));
+        const int k = (int)(((x & 2) ? inv4.y : inv4.x) >> ((x & 1) * 16)) & 0xFFFF;
         const int j = k >> 6;
         const int cbx = bx + (j % cxb), cby = by + (j / cxb);
         const int g = (cby >> 5) * fd.gxs + (cbx >> 5);

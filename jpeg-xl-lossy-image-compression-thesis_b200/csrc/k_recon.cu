@@ -113,15 +113,22 @@ __device__ void recon_transform(ReconShared& sh, int warp, bool active, int ox, 
     const float mul = inv_qac * (c == 0 ? A.inv_qm_x : (c == 1 ? 1.0f : A.inv_qm_b));
     const float cfl = c == 0 ? cfl_x : cfl_b;
     if (gl < H) {
+      uint2 inv4 = make_uint2(0u, 0u);
+      float4 dq4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       for (int x = 0; x < W; ++x) {
         const int pos = gl * W + x;
-        const int k = inv[pos];
+        if ((x & 3) == 0) {   // scan indices and dequantisation weights of four positions per vector load
+          inv4 = __ldg(reinterpret_cast<const uint2*>(inv + pos));
+          dq4 = __ldg(reinterpret_cast<const float4*>(dq + (size_t)c * size + pos));
+        }
+        const int k = (int)(((x & 2) ? inv4.y : inv4.x) >> ((x & 1) * 16)) & 0xFFFF;
+        const float dqv = (x & 3) == 0 ? dq4.x : ((x & 3) == 1 ? dq4.y : ((x & 3) == 2 ? dq4.z : dq4.w));
         const int j = k >> 6;
         const int cbx = bx + (j % cxb), cby = by + (j / cxb);
         const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
         const size_t blk = (size_t)g * kGroupBlocks + (size_t)(cby & 31) * 32 + (cbx & 31);
         const int q = active ? (int)A.coeffs[(blk * 3 + slot) * 64 + (k & 63)] : 0;
-        float v = (dequant_bias(c, q) * dq[(size_t)c * size + pos]) * mul;
+        float v = (dequant_bias(c, q) * dqv) * mul;
         if (c != 1) v = __fmaf_rn(cfl, bufs[1][gl * kTPitch + x], v);
         bufs[c][gl * kTPitch + x] = v;
       }

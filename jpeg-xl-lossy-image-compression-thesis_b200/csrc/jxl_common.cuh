@@ -62,7 +62,7 @@ __device__ __forceinline__ float fast_pow2f(float x) {
 
 // cube root for x >= 0 (bit-hack estimate of x^(-1/3), three Newton steps, x * r^2)
 __device__ __forceinline__ float cbrt_pos(float x) {
-  if (!(x > 0.0f)) return 0.0f;
+  // (branch-free: x <= 0 or NaN is selected to 0 at the end; the early return cost a divergence bracket per call)
   float r = __uint_as_float(0x54A21D2Au - __float_as_uint(x) / 3u);
   const float x3 = x * (1.0f / 3.0f);
   const float k43 = 4.0f / 3.0f;
@@ -72,7 +72,8 @@ __device__ __forceinline__ float cbrt_pos(float x) {
     const float r4 = r2 * r2;
     r = __fmaf_rn(-x3, r4, k43 * r);
   }
-  return (r * r) * x;
+  const float y = (r * r) * x;
+  return x > 0.0f ? y : 0.0f;
 }
 
 // ---- 1-D scaled DCT-II on registers, same operation order as oracle/jxo_dct.cc ------------

@@ -473,6 +473,7 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint8_t* s_cmap = reinterpret_cast<uint8_t*>(s_info + (size_t)K * kAcAlphabet);          // [7425 -> 7440]
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_cmap + 7440);                          // [warps][34]
   uint2* s_ops = reinterpret_cast<uint2*>(s_stage + kAnsWarps * kStageWords);                // [warps][2][32]
+  uint32_t* s_states = reinterpret_cast<uint32_t*>(s_ops + kAnsWarps * 64);                  // [warps][32]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   {
     const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
@@ -500,6 +501,7 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
   uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
   uint2* ops = s_ops + warp * 64;                          // two slots of 32 per-token chain operands (packed, rcp)
+  uint32_t* states = s_states + warp * 32;                 // the state every step of the current chunk started from
 
   // per-token operands of the chain: freq | (shared byte address of the symbol's reverse-map run) << 13, reciprocal;
   // and the token's extra bits
@@ -521,6 +523,24 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
     asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
     const bool emit = state > thr;
     if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
+    const uint32_t x2 = emit ? (state >> 16) : state;
+    const uint32_t q = __umulhi(x2, rc);
+    const uint32_t r = q * negf + x2;
+    const bool fix = r >= f;
+    const uint32_t a_lo = tab_a + 2 * r, a_hi = tab_b + 2 * r;
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(fix ? a_hi : a_lo));
+    state = ((fix ? q + 1 : q) << kAnsLogTabSize) + v;
+  };
+  // the same step for the pipelined chunks: instead of every lane testing `lane == j` (a compare and two selects per
+  // step), lane 0 stores the state the step started from; lane j reads states[j] after the chain and derives what its
+  // token pushed out from its own copy of the operands
+  auto step_rec = [&](uint32_t pk, uint32_t rc, int j) {
+    const uint32_t f = pk & 0x1FFF, tab_a = pk >> 13;
+    uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;
+    asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
+    const bool emit = state > thr;
+    if (lane == 0) states[j] = state;
     const uint32_t x2 = emit ? (state >> 16) : state;
     const uint32_t q = __umulhi(x2, rc);
     const uint32_t r = q * negf + x2;
@@ -585,11 +605,11 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   // ---- full chunks, software-pipelined: while the serial chain of chunk c runs (a dependent sequence that leaves
   // most issue slots empty), the same warp prepares the operands of chunk c + 1 and places the pieces of chunk c - 1
   const int full = n > 0 ? (n - m0) >> 5 : 0;
-  uint32_t nb_c = 0, bits_c = 0;
+  uint32_t nb_c = 0, bits_c = 0, pk_c = 4096u;   // this lane's token of the chunk whose chain runs next
   if (full > 0) {
-    uint32_t packed, rcp;
-    prep(tk[n - m0 - 1 - lane], true, packed, rcp, nb_c, bits_c);
-    ops[lane] = make_uint2(packed, rcp);
+    uint32_t rcp;
+    prep(tk[n - m0 - 1 - lane], true, pk_c, rcp, nb_c, bits_c);
+    ops[lane] = make_uint2(pk_c, rcp);
   }
   uint32_t tok_next = full > 1 ? tk[n - m0 - 32 - 1 - lane] : 0;
   for (int c = 0; c < full; ++c) {
@@ -599,32 +619,38 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
     uint32_t o16_c = 0; int emit_c = 0;
     PackState P;
     // (a) first quarter of the chain || operands of the next chunk
-    uint32_t nb_n = 0, bits_n = 0;
+    uint32_t nb_n = 0, bits_n = 0, pk_n = 4096u;
     {
-      uint32_t packed, rcp;
-      prep(tok_next, c + 1 < full, packed, rcp, nb_n, bits_n);
-      nxt[lane] = make_uint2(packed, rcp);
+      uint32_t rcp;
+      prep(tok_next, c + 1 < full, pk_n, rcp, nb_n, bits_n);
+      nxt[lane] = make_uint2(pk_n, rcp);
       const int in = n - m0 - 32 * (c + 2) - 1 - lane;
       tok_next = (c + 2 < full) ? tk[in] : 0;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    for (int j = 0; j < 8; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
     // (b) second quarter || prefix sum of the previous chunk's piece lengths, staging window cleared
     pack_a(nb_p, bits_p, o16_p, emit_p, valid_p, P);
 #pragma unroll
-    for (int j = 8; j < 16; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    for (int j = 8; j < 16; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
     __syncwarp();
     // (c) third quarter || the previous chunk's pieces OR-ed into the window
     pack_b(P);
 #pragma unroll
-    for (int j = 16; j < 24; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    for (int j = 16; j < 24; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
     __syncwarp();
     // (d) last quarter || finished words stored
     pack_c(P);
 #pragma unroll
-    for (int j = 24; j < 32; ++j) { const uint2 o = cur[j]; step(o.x, o.y, j, o16_c, emit_c); }
+    for (int j = 24; j < 32; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
+    __syncwarp();
+    {
+      const uint32_t my_state = states[lane];
+      o16_c = my_state & 0xFFFF;
+      emit_c = my_state > (((pk_c & 0x1FFF) << 20) - 1) ? 1 : 0;
+    }
     nb_p = nb_c; bits_p = bits_c; o16_p = o16_c; emit_p = emit_c; valid_p = true;
-    nb_c = nb_n; bits_c = bits_n;
+    nb_c = nb_n; bits_c = bits_n; pk_c = pk_n;
   }
   // ---- drain: the pieces of the last chunk whose chain has run
   if (n > 0) {
@@ -688,7 +714,7 @@ static void launch_ans_groups_w(const uint32_t* tokens, const uint32_t* token_co
                                 const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
                                 uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
   const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
-                      kAnsWarps * kStageWords * 4 + kAnsWarps * 64 * sizeof(uint2);
+                      kAnsWarps * kStageWords * 4 + kAnsWarps * 64 * sizeof(uint2) + kAnsWarps * 32 * 4;
   cudaFuncSetAttribute(k_ans_groups<kAnsWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int per_cta = kAnsWarps * (groups_per_warp < 1 ? 1 : groups_per_warp);
   cudaMemsetAsync(work_counter, 0, 4, s);

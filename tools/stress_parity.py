@@ -2,10 +2,12 @@
 path's codestream and quality statistics must equal the oracle's for every case.  Images mix the synthetic generator with
 random rectangles, pure noise, black and saturated areas.  Usage: python tools/stress_parity.py [cases] [seed]"""
 import importlib
+import os
 import sys
 import time
 
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 
 pkg = importlib.import_module("jpeg-xl-lossy-image-compression-thesis_b200")

@@ -469,19 +469,17 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   extern __shared__ __align__(16) uint8_t smem[];
   const int K = *num_clusters_p;
   uint16_t* s_rmap = reinterpret_cast<uint16_t*>(smem);                                  // [K][4096]
-  AnsSymInfo* s_info = reinterpret_cast<AnsSymInfo*>(smem + (size_t)K * kAnsTabSize * 2);  // [K][64]
-  uint8_t* s_cmap = reinterpret_cast<uint8_t*>(s_info + (size_t)K * kAcAlphabet);          // [7425 -> 7440]
+  // (the per-symbol info is only read by the lane-parallel operand preparation, which runs a chunk ahead of the chain:
+  // it stays in global memory / L1, and its 12 KB of shared memory hold 16-byte chain operands instead)
+  uint8_t* s_cmap = smem + (size_t)K * kAnsTabSize * 2;                                    // [7425 -> 7440]
   uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_cmap + 7440);                          // [warps][34]
-  uint2* s_ops = reinterpret_cast<uint2*>(s_stage + kAnsWarps * kStageWords);                // [warps][2][32]
+  uint4* s_ops = reinterpret_cast<uint4*>(s_stage + kAnsWarps * kStageWords);                // [warps][2][32]
   uint32_t* s_states = reinterpret_cast<uint32_t*>(s_ops + kAnsWarps * 64);                  // [warps][32]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   {
     const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
     uint4* dst = reinterpret_cast<uint4*>(s_rmap);
     for (int i = t; i < K * kAnsTabSize / 8; i += kAnsWarps * 32) dst[i] = src[i];
-    const uint2* si = reinterpret_cast<const uint2*>(info_g);
-    uint2* di = reinterpret_cast<uint2*>(s_info);
-    for (int i = t; i < K * kAcAlphabet; i += kAnsWarps * 32) di[i] = si[i];
     for (int i = t; i < kNumAcContexts; i += kAnsWarps * 32) s_cmap[i] = cmap_g[i];
   }
   __syncthreads();
@@ -500,27 +498,26 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t state = kAnsInitState;
   long long end_bit = (long long)kTokensPerGroupMax * 32;  // stream position where the next (earlier) piece ends
   uint32_t carry = 0;                                      // bits of the partially filled word containing end_bit
-  uint2* ops = s_ops + warp * 64;                          // two slots of 32 per-token chain operands (packed, rcp)
+  uint4* ops = s_ops + warp * 64;                          // two slots of 32 per-token chain operands (thr, -freq, rcp, table)
   uint32_t* states = s_states + warp * 32;                 // the state every step of the current chunk started from
 
-  // per-token operands of the chain: freq | (shared byte address of the symbol's reverse-map run) << 13, reciprocal;
-  // and the token's extra bits
-  auto prep = [&](uint32_t tkn, bool valid, uint32_t& packed, uint32_t& rcp, uint32_t& nb, uint32_t& bits) {
-    packed = 4096u; rcp = 0x00100000u; nb = 0; bits = 0;
+  // per-token operands of the chain — renormalisation threshold (freq << 20) - 1, -freq, reciprocal, shared byte address
+  // of the symbol's reverse-map run — and the token's extra bits
+  auto prep = [&](uint32_t tkn, bool valid, uint4& op, uint32_t& nb, uint32_t& bits) {
+    op = make_uint4(0xFFFFFFFFu, 0u - 4096u, 0x00100000u, rmap_saddr); nb = 0; bits = 0;
     if (valid) {
       const uint32_t cl = s_cmap[tkn >> 16];
       uint32_t tok;
       hybrid_encode(tkn & 0xFFFF, tok, nb, bits);
-      const AnsSymInfo si = s_info[cl * kAcAlphabet + tok];
-      packed = si.freq | ((rmap_saddr + 2u * (cl * kAnsTabSize + si.base)) << 13);
-      rcp = si.rcp;
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(info_g + cl * kAcAlphabet + tok));
+      const uint32_t f = raw.x & 0xFFFFu, base = raw.x >> 16;
+      op = make_uint4((f << 20) - 1, 0u - f, raw.y, rmap_saddr + 2u * (cl * kAnsTabSize + base));
     }
   };
-  // one chain step on operands (pk, rc); lane j records what step j pushed out
-  auto step = [&](uint32_t pk, uint32_t rc, int j, uint32_t& my_o16, int& my_emit) {
-    const uint32_t f = pk & 0x1FFF, tab_a = pk >> 13;
-    uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;   // all off the state chain
-    asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
+  // one chain step on operands op = (thr, -freq, rcp, table); lane j records what step j pushed out
+  auto step = [&](uint4 op, int j, uint32_t& my_o16, int& my_emit) {
+    const uint32_t thr = op.x, negf = op.y, rc = op.z, tab_a = op.w;
+    const uint32_t f = 0u - negf, tab_b = tab_a + 2 * negf;
     const bool emit = state > thr;
     if (lane == j) { my_o16 = state & 0xFFFF; my_emit = emit; }
     const uint32_t x2 = emit ? (state >> 16) : state;
@@ -535,10 +532,9 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   // the same step for the pipelined chunks: instead of every lane testing `lane == j` (a compare and two selects per
   // step), lane 0 stores the state the step started from; lane j reads states[j] after the chain and derives what its
   // token pushed out from its own copy of the operands
-  auto step_rec = [&](uint32_t pk, uint32_t rc, int j) {
-    const uint32_t f = pk & 0x1FFF, tab_a = pk >> 13;
-    uint32_t thr = (f << 20) - 1, negf = 0u - f, tab_b = tab_a - 2 * f;
-    asm("" : "+r"(negf)); asm("" : "+r"(tab_b)); asm("" : "+r"(thr));
+  auto step_rec = [&](uint4 op, int j) {
+    const uint32_t thr = op.x, negf = op.y, rc = op.z, tab_a = op.w;
+    const uint32_t f = 0u - negf, tab_b = tab_a + 2 * negf;
     const bool emit = state > thr;
     if (lane == 0) states[j] = state;
     const uint32_t x2 = emit ? (state >> 16) : state;
@@ -592,65 +588,68 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t nb_p = 0, bits_p = 0, o16_p = 0; int emit_p = 0;   // pieces of the chunk whose chain has run, not yet placed
   bool valid_p = false;
   if (n > 0) {
-    uint32_t packed, rcp;
+    uint4 op;
     const uint32_t tkn = lane < m0 ? tk[n - 1 - lane] : 0;
-    prep(tkn, lane < m0, packed, rcp, nb_p, bits_p);
+    prep(tkn, lane < m0, op, nb_p, bits_p);
     for (int j = 0; j < m0; ++j) {
-      const uint32_t pk = __shfl_sync(0xffffffffu, packed, j);
-      const uint32_t rc = __shfl_sync(0xffffffffu, rcp, j);
-      step(pk, rc, j, o16_p, emit_p);
+      uint4 o;
+      o.x = __shfl_sync(0xffffffffu, op.x, j); o.y = __shfl_sync(0xffffffffu, op.y, j);
+      o.z = __shfl_sync(0xffffffffu, op.z, j); o.w = __shfl_sync(0xffffffffu, op.w, j);
+      step(o, j, o16_p, emit_p);
     }
     valid_p = lane < m0;
   }
   // ---- full chunks, software-pipelined: while the serial chain of chunk c runs (a dependent sequence that leaves
   // most issue slots empty), the same warp prepares the operands of chunk c + 1 and places the pieces of chunk c - 1
   const int full = n > 0 ? (n - m0) >> 5 : 0;
-  uint32_t nb_c = 0, bits_c = 0, pk_c = 4096u;   // this lane's token of the chunk whose chain runs next
+  uint32_t nb_c = 0, bits_c = 0, thr_c = 0xFFFFFFFFu;   // this lane's token of the chunk whose chain runs next
   if (full > 0) {
-    uint32_t rcp;
-    prep(tk[n - m0 - 1 - lane], true, pk_c, rcp, nb_c, bits_c);
-    ops[lane] = make_uint2(pk_c, rcp);
+    uint4 op;
+    prep(tk[n - m0 - 1 - lane], true, op, nb_c, bits_c);
+    ops[lane] = op;
+    thr_c = op.x;
   }
   uint32_t tok_next = full > 1 ? tk[n - m0 - 32 - 1 - lane] : 0;
   for (int c = 0; c < full; ++c) {
-    const uint2* cur = ops + (c & 1) * 32;
-    uint2* nxt = ops + ((c + 1) & 1) * 32;
+    const uint4* cur = ops + (c & 1) * 32;
+    uint4* nxt = ops + ((c + 1) & 1) * 32;
     __syncwarp();   // operands of chunk c visible; stage free
     uint32_t o16_c = 0; int emit_c = 0;
     PackState P;
     // (a) first quarter of the chain || operands of the next chunk
-    uint32_t nb_n = 0, bits_n = 0, pk_n = 4096u;
+    uint32_t nb_n = 0, bits_n = 0, thr_n = 0xFFFFFFFFu;
     {
-      uint32_t rcp;
-      prep(tok_next, c + 1 < full, pk_n, rcp, nb_n, bits_n);
-      nxt[lane] = make_uint2(pk_n, rcp);
+      uint4 op;
+      prep(tok_next, c + 1 < full, op, nb_n, bits_n);
+      nxt[lane] = op;
+      thr_n = op.x;
       const int in = n - m0 - 32 * (c + 2) - 1 - lane;
       tok_next = (c + 2 < full) ? tk[in] : 0;
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
+    for (int j = 0; j < 8; ++j) { step_rec(cur[j], j); }
     // (b) second quarter || prefix sum of the previous chunk's piece lengths, staging window cleared
     pack_a(nb_p, bits_p, o16_p, emit_p, valid_p, P);
 #pragma unroll
-    for (int j = 8; j < 16; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
+    for (int j = 8; j < 16; ++j) { step_rec(cur[j], j); }
     __syncwarp();
     // (c) third quarter || the previous chunk's pieces OR-ed into the window
     pack_b(P);
 #pragma unroll
-    for (int j = 16; j < 24; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
+    for (int j = 16; j < 24; ++j) { step_rec(cur[j], j); }
     __syncwarp();
     // (d) last quarter || finished words stored
     pack_c(P);
 #pragma unroll
-    for (int j = 24; j < 32; ++j) { const uint2 o = cur[j]; step_rec(o.x, o.y, j); }
+    for (int j = 24; j < 32; ++j) { step_rec(cur[j], j); }
     __syncwarp();
     {
       const uint32_t my_state = states[lane];
       o16_c = my_state & 0xFFFF;
-      emit_c = my_state > (((pk_c & 0x1FFF) << 20) - 1) ? 1 : 0;
+      emit_c = my_state > thr_c ? 1 : 0;
     }
     nb_p = nb_c; bits_p = bits_c; o16_p = o16_c; emit_p = emit_c; valid_p = true;
-    nb_c = nb_n; bits_c = bits_n; pk_c = pk_n;
+    nb_c = nb_n; bits_c = bits_n; thr_c = thr_n;
   }
   // ---- drain: the pieces of the last chunk whose chain has run
   if (n > 0) {
@@ -713,8 +712,8 @@ template <int kAnsWarps>
 static void launch_ans_groups_w(const uint32_t* tokens, const uint32_t* token_counts, const uint8_t* cmap, const void* info,
                                 const uint16_t* rmap, const int* num_clusters, uint32_t* work_counter, int groups_per_warp,
                                 uint32_t* out_arena, unsigned long long* start_bit, int num_groups, cudaStream_t s) {
-  const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + (size_t)kMaxClusters * kAcAlphabet * sizeof(AnsSymInfo) + 7440 +
-                      kAnsWarps * kStageWords * 4 + kAnsWarps * 64 * sizeof(uint2) + kAnsWarps * 32 * 4;
+  const size_t smem = (size_t)kMaxClusters * kAnsTabSize * 2 + 7440 + kAnsWarps * kStageWords * 4 + kAnsWarps * 64 * sizeof(uint4) +
+                      kAnsWarps * 32 * 4;
   cudaFuncSetAttribute(k_ans_groups<kAnsWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int per_cta = kAnsWarps * (groups_per_warp < 1 ? 1 : groups_per_warp);
   cudaMemsetAsync(work_counter, 0, 4, s);

@@ -27,7 +27,7 @@ struct jxlb200_ctx {
   bool use_copy_stream = true;
   int ans_warps_single = 8;           // warps per rANS CTA for a single image (4: 2.51 ms, 8: 2.45 ms, 16: 2.65 ms per 4K frame) ($JXLB200_ANS_WARPS_SINGLE)
   int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
-  int ans_gpw = 3;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
+  int ans_gpw = 2;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::string err;
   Encoder* pipe(int i) { return i == 0 ? &enc : extra[i - 1]; }
 };

@@ -343,9 +343,9 @@ def main():
                                   "ms": float(mean_stage[STAGE_INDEX["ans"]]), "tokens": int(last_stats.num_tokens),
                                   "Mtokens_per_s": (last_stats.num_tokens / 1e6) / (float(mean_stage[STAGE_INDEX["ans"]]) / 1e3)
                                   if mean_stage[STAGE_INDEX["ans"]] > 0 else 0.0,
-                                  "bound": "dependency latency of the longest group's chain (~115 cycles per token after "
-                                           "software pipelining; ncu profiles/r01h: fixed-latency waits 42 %, shared-memory "
-                                           "loads 19 %, issue 23 %), not bandwidth"},
+                                  "bound": "dependency latency of the longest group's chain (~110 cycles per token, 21 warp "
+                                           "instructions per token; ncu profiles/r01l: fixed-latency waits 43 %, shared-memory "
+                                           "loads 25 %, issue 21 %), not bandwidth"},
                 "note": "per-kernel times from single-image encodes (one stream); the largest stage, the per-group "
                         "rANS chains (ans), is serial-latency bound, not bandwidth bound: see profiles/"}
         line = {

@@ -324,7 +324,8 @@ def test_quality_stats_batch_and_full_size(pkg, oracle, encoder):
 
 def test_randomised_parity_sweep():
     """60 random (size, content, distance, effort, proposal, flags) cases: codestream and quality statistics equal the
-    oracle's (tools/stress_parity.py runs the same sweep at any length; 3 300 cases were clean in round 1)."""
+    oracle's (tools/stress_parity.py runs the same sweep at any length; 5 300 cases were clean in round 1, 2 000 of them on
+    the round's last commit)."""
     import subprocess, sys, os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_parity.py"), "60", "11"], capture_output=True, text=True)

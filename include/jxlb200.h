@@ -11,7 +11,7 @@
  * called once per (image, distance, effort) from
  *   JXLCompressionBenchmark::run   benchmark-jpegxl/src/benchmark.rs:654-660
  * with failures mapped to "skip" (benchmark.rs:661-677).  Which proposal is active
- * is not an argument there: it is "which proposals/*.diff was applied before libjxl
+ * is not an argument there: it is "which proposals/NAME.diff was applied before libjxl
  * was rebuilt" (benchmark.rs:460-484, docker_manager.rs:303-368).  Here it is a
  * runtime enum.
  *
@@ -35,7 +35,7 @@ extern "C" {
 
 typedef struct jxlb200_ctx jxlb200_ctx;
 
-/* Which libjxl patch of the thesis is emulated (proposals/*.diff). */
+/* Which libjxl patch of the thesis is emulated (proposals/NAME.diff). */
 enum {
   JXLB200_PROPOSAL_NONE = 0,             /* unpatched libjxl ("main", context.rs:17)           */
   JXLB200_PROPOSAL_PARTITIONING = 1,     /* proposals/homogeneity-partitioning.diff:272-276     */

@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 
 def test_exports_match_header(pkg):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,3 +36,34 @@ def test_no_gpu_means_no_encoder(pkg):
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("Encoder() must fail loudly without a GPU")
+
+
+def _build_c_client(tmp_path):
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "jpeg-xl-lossy-image-compression-thesis_b200")
+    exe = os.path.join(str(tmp_path), "cabi_client")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cabi_client.c"), "-o", exe, "-L", libdir, "-ljxlb200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/jxlb200.h compiles as pedantic C99 and a C program links against libjxlb200.so; without a GPU the client
+    sees jxlb200_create() == NULL (no CPU fallback) and exits cleanly."""
+    import subprocess
+    import torch
+    exe = _build_c_client(tmp_path)
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "returned NULL" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_encodes(tmp_path):
+    """The same C program on a B200: encode, stats, error contract, release."""
+    import subprocess
+    r = subprocess.run([_build_c_client(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("ok:"), r.stdout + r.stderr

@@ -107,3 +107,23 @@ def test_oracle_rejects_bad_params(oracle, pkg):
     assert oracle.encode(img, 0.0, 7).error != ""
     assert oracle.encode(img, 1.0, 0).error != ""
     assert oracle.encode(img, 1.0, 7, 9).error != ""
+
+
+def test_xyb_matches_the_float64_definition(oracle, pkg):
+    """Stage U1 against the published definition evaluated in float64 (exact sRGB EOTF, opsin matrix and bias of
+    SURVEY 8a row U1, exact cube roots): the oracle's fp32 path with its rational-polynomial EOTF and Newton cube root
+    stays within the north star's 1e-5 of it on a whole synthetic image (absolute, against values of order 1)."""
+    img = pkg.synth_image(160, 96, 4)
+    f = oracle.encode(img, 1.0, 7, 0, 3)
+    d = oracle.dims(160, 96)
+    xyb = f.dump("xyb").reshape(3, d["ys_pad"], d["pitch"])[:, :96, :160].astype(np.float64)
+    f.close()
+    v = img.astype(np.float64) / 255.0
+    lin = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.055) ** 2.4)
+    m = np.array([[0.30, 0.622, 0.078], [0.23, 0.692, 0.078],
+                  [0.24342268924547819, 0.20476744424496821, 0.55180986650955360]])
+    bias = 0.0037930732552754493
+    mix = np.maximum(lin @ m.T + bias, 0.0)
+    lms = np.cbrt(mix) - np.cbrt(bias)
+    want = np.stack([(lms[..., 0] - lms[..., 1]) / 2, (lms[..., 0] + lms[..., 1]) / 2, lms[..., 2]])
+    assert np.abs(xyb - want).max() < 1e-5

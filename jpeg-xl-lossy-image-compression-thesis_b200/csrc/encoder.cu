@@ -46,11 +46,20 @@ bool Encoder::Init(int device, std::string* err) {
     if (!d_weights_[k].Reserve(w.size()) || !d_dequant_[k].Reserve(w.size())) { *err = "alloc"; return false; }
     CUDA_OK(cudaMemcpy(d_weights_[k].p, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(d_dequant_[k].p, dq.data(), dq.size() * 4, cudaMemcpyHostToDevice));
+    if (k == 6 || k == 8 || k == 12) {
+      // lane order of the WIDE strategy of the kind: [c][hf][vf] (the stored table is [c][vf][hf], H rows of W)
+      const size_t W = k == 6 ? 16 : (k == 8 ? 32 : 64), H = W / 2;
+      std::vector<float> wt(w.size()), dt(w.size());
+      for (size_t c = 0; c < 3; ++c) for (size_t y = 0; y < H; ++y) for (size_t x = 0; x < W; ++x) {
+        wt[c * W * H + x * H + y] = w[c * W * H + y * W + x];
+        dt[c * W * H + x * H + y] = dq[c * W * H + y * W + x];
+      }
+      if (!d_weights_t_[k].Reserve(wt.size()) || !d_dequant_t_[k].Reserve(dt.size())) { *err = "alloc"; return false; }
+      CUDA_OK(cudaMemcpy(d_weights_t_[k].p, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(d_dequant_t_[k].p, dt.data(), dt.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
   {
-    // default: two threads per block with cp.async-staged tiles (k_dct8_v4.cu); JXLB200_DCT8=1 selects the first
-    // design (8 lanes per block, k_dct_quant.cu) for comparison
-    if (const char* e = getenv("JXLB200_DCT8")) dct8_variant_ = atoi(e);
     if (const char* e = getenv("JXLB200_DCT8_ROWS")) dct8_rows_ = atoi(e);
     if (const char* e = getenv("JXLB200_DCT8_TPS")) dct8_tps_ = atoi(e);
   }
@@ -59,8 +68,6 @@ bool Encoder::Init(int device, std::string* err) {
     host_natural_order(0, &order);
     uint8_t izz[64];
     for (int k = 0; k < 64; ++k) izz[order[k]] = (uint8_t)k;
-    if (!d_izz8_.Reserve(64)) { *err = "alloc"; return false; }
-    CUDA_OK(cudaMemcpy(d_izz8_.p, izz, 64, cudaMemcpyHostToDevice));
     std::vector<float> bias(dct8_v4_bias_entries());
     std::vector<uint8_t> lut(2 * 4 * 256);
     dct8_v4_host_tables(izz, bias.data(), lut.data());
@@ -88,7 +95,7 @@ bool Encoder::Init(int device, std::string* err) {
   CUDA_OK(cudaMallocHost(&h_out_info_, 40 * sizeof(unsigned long long)));
   {
     // inverse natural coefficient orders of the order classes the search can emit
-    static const int rep[13] = {0, 3, 4, 5, 6, 8, 10, -1, -1, -1, -1, -1, -1};
+    static const int rep[13] = {0, 3, 4, 5, 6, 8, 10, 18, 19, -1, -1, -1, -1};
     for (int o = 0; o < 13; ++o) {
       if (rep[o] < 0) continue;
       std::vector<uint16_t> order;
@@ -97,11 +104,22 @@ bool Encoder::Init(int device, std::string* err) {
       for (size_t k = 0; k < order.size(); ++k) inv[order[k]] = (uint16_t)k;
       if (!d_inv_order_[o].Reserve(inv.size())) { *err = "alloc"; return false; }
       CUDA_OK(cudaMemcpy(d_inv_order_[o].p, inv.data(), inv.size() * 2, cudaMemcpyHostToDevice));
+      if (o == 4 || o == 6 || o == 8) {   // wide strategy of the class: positions in [hf][vf] lane order
+        const size_t W = o == 4 ? 16 : (o == 6 ? 32 : 64), H = W / 2;
+        std::vector<uint16_t> invt(inv.size());
+        for (size_t y = 0; y < H; ++y) for (size_t x = 0; x < W; ++x) invt[x * H + y] = inv[y * W + x];
+        const int slot = o == 4 ? 13 : (o == 6 ? 14 : 15);
+        if (!d_inv_order_[slot].Reserve(invt.size())) { *err = "alloc"; return false; }
+        CUDA_OK(cudaMemcpy(d_inv_order_[slot].p, invt.data(), invt.size() * 2, cudaMemcpyHostToDevice));
+      }
     }
   }
   if (!d_cvx_.Reserve(27) || !d_cvy_.Reserve(27) || !d_q_.Reserve(1)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_cvx_.p, kCoveredX, 27, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d_cvy_.p, kCoveredY, 27, cudaMemcpyHostToDevice));
+  // the uploads above come from pageable memory on the legacy stream, the pipeline runs on a non-blocking stream that is
+  // not ordered against it: make sure every table has landed before the first kernel can read it
+  CUDA_OK(cudaDeviceSynchronize());
   return true;
 }
 
@@ -111,9 +129,10 @@ void Encoder::Destroy() {
   if (stream_) cudaStreamSynchronize(stream_);
   if (ev_copy_) { cudaEventDestroy(ev_copy_); ev_copy_ = nullptr; }
   d_lut_.Release();
-  for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); }
-  d_izz8_.Release(); d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
-  for (int o = 0; o < 13; ++o) d_inv_order_[o].Release();
+  for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); d_weights_t_[k].Release(); d_dequant_t_[k].Release(); }
+  d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
+  d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
+  for (int o = 0; o < 16; ++o) d_inv_order_[o].Release();
   d_rgb_.Release(); d_xyb_.Release(); d_mask1x1_.Release(); d_pre_.Release(); d_qf_.Release(); d_mask_.Release();
   d_homog_.Release(); d_acs_entropy_.Release(); d_acs_.Release(); d_raw_qf_.Release(); d_cmap_.Release();
   d_coeffs_.Release(); d_dc_quant_.Release(); d_nzeros_.Release(); d_nzcount_.Release(); d_lastk_.Release(); d_q_.Release();
@@ -141,7 +160,9 @@ bool Encoder::Reserve(const FrameDim& fd, std::string* err) {
             d_acs_entropy_.Reserve(nblk) && d_acs_.Reserve(nblk) && d_raw_qf_.Reserve(nblk) &&
             d_cmap_.Reserve((size_t)2 * fd.txs * fd.tys) &&
             d_coeffs_.Reserve((size_t)fd.num_groups * kGroupBlocks * 192) && d_dc_quant_.Reserve(3 * nblk) &&
-            d_nzeros_.Reserve(3 * nblk) && d_nzcount_.Reserve(3 * nblk) && d_lastk_.Reserve(3 * nblk);
+            d_nzeros_.Reserve(3 * nblk) && d_nzcount_.Reserve(3 * nblk) && d_lastk_.Reserve(3 * nblk) &&
+            d_acs_work_.Reserve(acs_work_floats(fd)) && d_acs_jobs_.Reserve(acs_work_jobs(fd)) &&
+            d_coeff_lists_.Reserve(coeff_list_words(fd));
   // modular element space: one fixed-capacity run per DC group (k_modular.cu)
   h_dgs_.clear();
   uint32_t elem = 0, blocks = 0;
@@ -172,6 +193,7 @@ bool Encoder::Reserve(const FrameDim& fd, std::string* err) {
     if (cudaMemcpy(d_dgs_.p, h_dgs_.data(), h_dgs_.size() * sizeof(DcGroupInfo), cudaMemcpyHostToDevice) != cudaSuccess) {
       *err = "memcpy"; return false;
     }
+    if (cudaDeviceSynchronize() != cudaSuccess) { *err = "memcpy"; return false; }   // (same ordering argument as in Init)
     dgs_w_ = fd.xsize; dgs_h_ = fd.ysize;
   }
   return true;
@@ -274,7 +296,9 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   const bool search = !(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5;
   CUDA_OK(cudaMemsetAsync(d_cmap_.p, 0, (size_t)2 * fd.txs * fd.tys, stream_));
   AcsTables tables;
-  for (int k = 0; k < 17; ++k) { tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; }
+  for (int k = 0; k < 17; ++k) {
+    tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; tables.wT[k] = d_weights_t_[k].p; tables.dqT[k] = d_dequant_t_[k].p;
+  }
   if (search) {
     AcsParams ap;
     const float ratio = (p.distance + 0.1373f) / 1.1373f;
@@ -286,7 +310,9 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
     ap.cmap_x = 0.0f; ap.cmap_b = 1.0f;   // colour correlation map is the default (all tiles 0)
     ap.partitioning = p.proposal == JXLB200_PROPOSAL_PARTITIONING || p.proposal == JXLB200_PROPOSAL_COMBINED;
     ap.factored_entropy = p.proposal == JXLB200_PROPOSAL_FACTORED_ENTROPY || p.proposal == JXLB200_PROPOSAL_COMBINED;
-    launch_acs(X, Y, B, d_mask1x1_.p, d_qf_.p, d_homog_.p, fd, ap, tables, d_acs_.p, d_acs_entropy_.p, stream_);
+    ap.speed_tier = 10 - (int)p.effort;
+    launch_acs(X, Y, B, d_mask1x1_.p, d_qf_.p, d_homog_.p, fd, ap, tables, d_acs_work_.p, d_acs_jobs_.p, d_acs_.p, d_acs_entropy_.p,
+               stream_);
   } else {
     CUDA_OK(cudaMemsetAsync(d_acs_.p, 0x80, nblk, stream_));
     CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));
@@ -295,20 +321,15 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   CUDA_OK(cudaEventRecord(ev_[5], stream_));
   // K7: transform + quantise
   if (search) {
-    const uint16_t* inv_order[13];
-    for (int o = 0; o < 13; ++o) inv_order[o] = d_inv_order_[o].p;
+    const uint16_t* inv_order[16];
+    for (int o = 0; o < 16; ++o) inv_order[o] = d_inv_order_[o].p;
     launch_coeff_general(X, Y, B, d_acs_.p, fd, d_q_.p, tables, inv_order, d_cmap_.p, x_qm_mul_, b_qm_mul_,
                          p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
-                         stream_);
+                         d_coeff_lists_.p, stream_);
   } else {
-    if (dct8_variant_ == 4)
       launch_dct8_quant_v4(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_bias8_.p, d_lastlut8_.p, d_cmap_.p,
                            x_qm_mul_, b_qm_mul_, p.effort >= 5 ? 1 : 0, dct8_rows_, dct8_tps_, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p,
                            d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
-    else
-      launch_dct8_quant(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_izz8_.p, d_cmap_.p, x_qm_mul_,
-                        b_qm_mul_, p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p,
-                        d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
   // K8: tokens + per-context histograms
@@ -357,11 +378,13 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   CUDA_OK(cudaEventRecord(ev_[11], stream_));
   // K13 (optional): reconstruction error of the coded frame against the input, for stats.sse / stats.psnr
   if (p.flags & JXLB200_FLAG_QUALITY) {
-    const uint16_t* inv_order[13];
-    for (int o = 0; o < 13; ++o) inv_order[o] = d_inv_order_[o].p;
+    const uint16_t* inv_order[16];
+    for (int o = 0; o < 16; ++o) inv_order[o] = d_inv_order_[o].p;
+    if (!d_recon_xyb_.Reserve(3 * plane)) { *err = "device allocation failed"; return false; }
+    if (!search) launch_coeff_lists(d_acs_.p, fd, d_coeff_lists_.p, stream_);   // (the search path binned the map already)
     launch_recon_sse(fd, d_q_.p, tables, inv_order, d_cmap_.p, 1.0f / powf(1.25f, (float)(x_qm_scale_ - 2)),
                      1.0f / powf(1.25f, (float)(b_qm_scale_ - 2)), d_acs_.p, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_rgb, stride,
-                     d_recon_tab_.p, d_out_info_.p + 36, stream_);
+                     d_recon_tab_.p, d_coeff_lists_.p, d_recon_xyb_.p, d_out_info_.p + 36, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[12], stream_));
   CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));

@@ -52,7 +52,7 @@ class Encoder {
   bool Reserve(const FrameDim& fd, std::string* err);
   bool Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, std::string* err);
   bool in_flight_ = false;
-  int dct8_variant_ = 4, dct8_rows_ = 2, dct8_tps_ = 512;   // DCT8 kernel: 4 = two threads per block (default), 1 = 8 lanes per block
+  int dct8_rows_ = 2, dct8_tps_ = 512;   // k_dct8_quant_v4 launch shape
   int ans_groups_per_warp_ = 1, ans_warps_ = 8;
   unsigned launches_ = 0;
 
@@ -71,10 +71,10 @@ class Encoder {
   DevBuf<float> d_lut_, d_recon_tab_;
   DevBuf<float> d_weights_[17];
   DevBuf<float> d_dequant_[17];
-  DevBuf<uint8_t> d_izz8_;        // DCT8: position -> scan index
+  DevBuf<float> d_weights_t_[17], d_dequant_t_[17];   // transposed ([hf][vf] of the wide strategy) for kinds 6, 8, 12
   DevBuf<float> d_bias8_;         // k_dct8_v4: Y dequantisation bias per |q|
   DevBuf<uint8_t> d_lastlut8_;    // k_dct8_v4: last scan index per (lane half, mask byte, byte value)
-  DevBuf<uint16_t> d_inv_order_[13];  // per order class: coefficient position -> scan index
+  DevBuf<uint16_t> d_inv_order_[16];  // per order class: coefficient position -> scan index; [13..15]: classes 4 / 6 / 8 transposed (wide)
   DevBuf<uint8_t> d_cvx_, d_cvy_;
   // per-frame arenas
   DevBuf<uint8_t> d_rgb_;
@@ -88,6 +88,10 @@ class Encoder {
   DevBuf<uint8_t> d_nzeros_;
   DevBuf<uint16_t> d_nzcount_, d_lastk_;
   DevBuf<QuantDev> d_q_;
+  DevBuf<float> d_acs_work_;      // candidate-value tables of the AC-strategy search
+  DevBuf<uint32_t> d_acs_jobs_;   // its non-aligned work lists
+  DevBuf<uint32_t> d_coeff_lists_;  // first blocks per strategy (k_coeff / k_recon)
+  DevBuf<float> d_recon_xyb_;       // reconstructed XYB planes (JXLB200_FLAG_QUALITY only)
   // entropy stage: AC tokens / histograms / clusters / ANS tables / group streams
   DevBuf<int> d_log2lut_;
   DevBuf<uint32_t> d_tokens_, d_token_counts_, d_hist_, d_cluster_hist_, d_hdr_bits_, d_hdr_len_, d_group_arena_;

@@ -100,6 +100,17 @@ static const Bands kB4x8 = {4, {{2198.050556016380522f, -0.96269623020744692f, -
                                 {764.3655248643528689f, -0.92630200888366945f, -0.9675229603596517f, -0.27845290869168118f},
                                 {527.107573587542228f, -1.4594385811273854f, -1.450082094097871593f, -1.5843722511996204f}}};
 
+static const Bands kB64 = {8, {{0.9f * 26629.073922049845f, -1.025f, -0.78f, -0.65012f, -0.19041574084286472f, -0.20819395464f, -0.421064f, -0.32733845535848671f},
+                               {0.9f * 9311.3238710010046f, -0.3041958212306401f, -0.3633036457487539f, -0.35660379990111464f, -0.3443074455424403f, -0.33699592683512467f, -0.30180866526242109f, -0.27321683125358037f},
+                               {0.9f * 4992.2486445538634f, -1.2f, -1.2f, -0.8f, -0.7f, -0.7f, -0.4f, -0.5f}}};
+static const Bands kB32x64 = {8, {{0.65f * 23629.073922049845f, -1.025f, -0.78f, -0.65012f, -0.19041574084286472f, -0.20819395464f, -0.421064f, -0.32733845535848671f},
+                                  {0.65f * 8611.3238710010046f, -0.3041958212306401f, -0.3633036457487539f, -0.35660379990111464f, -0.3443074455424403f, -0.33699592683512467f, -0.30180866526242109f, -0.27321683125358037f},
+                                  {0.65f * 4492.2486445538634f, -1.2f, -1.2f, -0.8f, -0.7f, -0.7f, -0.4f, -0.5f}}};
+// IDENTITY / DCT2X2 parameter sets (libjxl QuantEncoding::Identity / DCT2 library values)
+static const float kIdW[3][3] = {{280.0f, 3160.0f, 3160.0f}, {60.0f, 864.0f, 864.0f}, {18.0f, 200.0f, 200.0f}};
+static const float kDct2W[3][6] = {{3840.0f, 2560.0f, 1280.0f, 640.0f, 480.0f, 300.0f}, {960.0f, 640.0f, 320.0f, 180.0f, 140.0f, 120.0f},
+                                   {640.0f, 320.0f, 128.0f, 64.0f, 32.0f, 16.0f}};
+
 static void band_weights(int rows, int cols, const Bands& bp, float* out) {
   for (int c = 0; c < 3; ++c) {
     float bands[8];
@@ -135,6 +146,30 @@ int host_quant_weights(int kind, std::vector<float>* w) {
     case 6: bp = &kB16x8; rows = 8; cols = 16; break;
     case 7: bp = &kB32x8; rows = 8; cols = 32; break;
     case 8: bp = &kB32x16; rows = 16; cols = 32; break;
+    case 11: bp = &kB64; rows = cols = 64; break;
+    case 12: bp = &kB32x64; rows = 32; cols = 64; break;
+    case 1: {
+      w->assign(192, 0.0f);
+      for (int c = 0; c < 3; ++c) {
+        for (int i = 0; i < 64; ++i) (*w)[c * 64 + i] = kIdW[c][0];
+        (*w)[c * 64 + 1] = kIdW[c][1]; (*w)[c * 64 + 8] = kIdW[c][1]; (*w)[c * 64 + 9] = kIdW[c][2];
+      }
+      return 64;
+    }
+    case 2: {
+      w->assign(192, 0.0f);
+      for (int c = 0; c < 3; ++c) {
+        float* o = &(*w)[c * 64];
+        o[0] = 2989.0f;   // the DC position is never quantised with this table
+        o[1] = o[8] = kDct2W[c][0];
+        o[9] = kDct2W[c][1];
+        for (int y = 0; y < 2; ++y) for (int x = 2; x < 4; ++x) { o[y * 8 + x] = kDct2W[c][2]; o[x * 8 + y] = kDct2W[c][2]; }
+        for (int y = 2; y < 4; ++y) for (int x = 2; x < 4; ++x) o[y * 8 + x] = kDct2W[c][3];
+        for (int y = 0; y < 4; ++y) for (int x = 4; x < 8; ++x) { o[y * 8 + x] = kDct2W[c][4]; o[x * 8 + y] = kDct2W[c][4]; }
+        for (int y = 4; y < 8; ++y) for (int x = 4; x < 8; ++x) o[y * 8 + x] = kDct2W[c][5];
+      }
+      return 64;
+    }
     case 3: {
       float w4[48];
       band_weights(4, 4, kB4, w4);

@@ -1,31 +1,67 @@
-// K7 (general) — forward transform, DC extraction and adaptive quantisation for every AC strategy the
-// search can pick (stage U5: libjxl enc_group.cc ComputeCoefficients / AdjustQuantBlockAC /
-// QuantizeBlockAC / QuantizeRoundtripYBlockAC, enc_modular.cc AddVarDCTDC, dct_util
-// DCFromLowestFrequencies [UPSTREAM]); same arithmetic and operation order as oracle/jxo_coef.cc.
-// The DCT8-only frame (BASELINE config 2) keeps its specialised kernel (k_dct_quant.cu).
+// K7 (general) — forward transform, DC extraction and adaptive quantisation for every AC strategy the search can pick
+// (stage U5: libjxl enc_group.cc ComputeCoefficients / AdjustQuantBlockAC / QuantizeBlockAC / QuantizeRoundtripYBlockAC,
+// enc_modular.cc AddVarDCTDC, dct_util DCFromLowestFrequencies [UPSTREAM]); same arithmetic and operation order as
+// oracle/jxo_coef.cc.  The DCT8-only frame (BASELINE config 2) keeps its specialised kernel (k_dct8_v4.cu).
 //
-// One CTA per 32x32-pixel square: the XYB tile is staged in shared memory, every warp takes the
-// transforms whose first block lies in the square round-robin.  Lane y of the transform's group owns
-// coefficient row y (transforms.cuh); block-wide sums of the heuristics are xor-butterflies over the
-// rows.  Quantised coefficients go to the group arena in scan order through the inverse natural
-// order table of the strategy's class.
+// The strategy map is first binned (k_coeff_lists: one list of first blocks per strategy, warp-aggregated appends), so
+// that every warp of the transform kernels runs ONE strategy's code:
+//   k_coeff8<S>     8x8 strategies, one thread per block, the block in registers (fwd8x8); the scan-order permutation
+//                   of the 64 quantised values is resolved at compile time, a channel leaves as eight 16-byte stores
+//   k_coeffsq<N, M> 16 / 32 / 64-sized strategies, one lane group of N lanes per transform (SquareXform): lane hf owns
+//                   every vertical frequency of horizontal frequency hf from the column pass to the output, the
+//                   heuristics' block sums are xor-butterflies over the lanes; X and B wait in shared memory while Y is
+//                   quantised; only non-zero coefficients are scattered into the (pre-zeroed) scan-order arena
 #include "transforms.cuh"
 #include "kernels.h"
 
 namespace jxlb {
 
-#ifndef JXLB_COEFF_WARPS
-#define JXLB_COEFF_WARPS 4
-#endif
-constexpr int kCoeffWarps = JXLB_COEFF_WARPS;
+// list ids: six 8x8 strategies, then (tall, wide, square) of the three larger levels
+enum { kListDCT = 0, kListID, kList2X2, kList4X4, kList4X8, kList8X4, kList16Tall, kList16Wide, kList16Sq, kList32Tall, kList32Wide,
+       kList32Sq, kList64Tall, kList64Wide, kList64Sq, kNumLists };
 
-struct CoeffShared {
-  float px[3][32 * kTPitch];
-  float buf[kCoeffWarps][3][32 * kTPitch];   // per warp: X, Y, B coefficient rows (transforms and quantisation work in place)
-  // channel-parallel path (32-lane transforms): per-channel adjusted quant, Y's thresholds, per-channel DC values
-  int cp_q[3];
-  float cp_thr[4];
-  float cp_dc[3][16];
+__device__ __forceinline__ int list_of_strategy(int s) {
+  switch (s) {
+    case kStratDCT: return kListDCT;       case kStratIDENTITY: return kListID;    case kStratDCT2X2: return kList2X2;
+    case kStratDCT4X4: return kList4X4;    case kStratDCT4X8: return kList4X8;     case kStratDCT8X4: return kList8X4;
+    case kStratDCT16X8: return kList16Tall; case kStratDCT8X16: return kList16Wide; case kStratDCT16X16: return kList16Sq;
+    case kStratDCT32X16: return kList32Tall; case kStratDCT16X32: return kList32Wide; case kStratDCT32X32: return kList32Sq;
+    case kStratDCT64X32: return kList64Tall; case kStratDCT32X64: return kList64Wide; case kStratDCT64X64: return kList64Sq;
+    default: return -1;
+  }
+}
+
+size_t coeff_list_words(const FrameDim& fd) { return 16 + (size_t)kNumLists * fd.bxs * fd.bys; }
+
+__global__ void __launch_bounds__(256) k_coeff_lists(const uint8_t* __restrict__ acs, int nblk, uint32_t* __restrict__ lists) {
+  const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
+  int li = -1;
+  if (i < nblk) { const uint8_t a = acs[i]; if (a & 0x80) li = list_of_strategy(a & 0x7f); }
+  // one atomic per (warp, list)
+  unsigned todo = __ballot_sync(0xffffffffu, li >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int l0 = __shfl_sync(0xffffffffu, li, leader);
+    const unsigned same = __ballot_sync(0xffffffffu, li == l0);
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&lists[l0], (unsigned)__popc(same));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (li == l0) lists[16 + (size_t)l0 * nblk + base + __popc(same & ((1u << lane) - 1))] = (uint32_t)i;
+    todo &= ~same;
+  }
+}
+
+struct CoeffArgs {
+  const float* X; const float* Y; const float* B;
+  FrameDim fd;
+  const QuantDev* qd;
+  const float* w; const float* dq;          // tables of the strategy in lane order ([hf][vf]; see AcsTables)
+  const uint16_t* inv;                      // coefficient position (same lane order) -> scan index
+  const int8_t* cmap;
+  float x_qm_mul, b_qm_mul;
+  int adjust;
+  int32_t* raw_qf; int16_t* coeffs; int16_t* dc_quant; uint8_t* nzeros; uint16_t* nzcount; uint16_t* lastk;
+  const uint32_t* list; const uint32_t* count;
 };
 
 __device__ __forceinline__ float quant_bias(int c, int q) {
@@ -37,86 +73,44 @@ __device__ __forceinline__ float quant_bias(int c, int q) {
   const float fq = (float)q;
   return fq - 0.145f / fq;
 }
-
 __device__ __forceinline__ float clamp1(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int16_t sat16(int v) { return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); }
 
-// oracle AdjustQuantBlockAC for the group's lanes (lane y = coefficient row y); returns the adjusted quant
+// AddVarDCTDC quantisation of one block's DC values (Y first; X / B with the default 0 / 1.0 base correlation)
+__device__ __forceinline__ void store_dc(const CoeffArgs& A, size_t bj, float dcX, float dcY, float dcB) {
+  const size_t nblk = (size_t)A.fd.bxs * A.fd.bys;
+  const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
+  const int quant_dc = A.qd->quant_dc;
+  const float gsq = scale * (float)quant_dc;
+  const float inv_quant_dc = inv_gs / (float)quant_dc;
+  const float y_factor = inv_quant_dc * (1.0f / 512.0f);
+  const float qy = roundf(dcY * (512.0f * gsq));
+  const float qx = roundf((dcX - qy * (y_factor * 0.0f)) * (4096.0f * gsq));
+  const float qb = roundf((dcB - qy * (y_factor * 1.0f)) * (256.0f * gsq));
+  A.dc_quant[0 * nblk + bj] = sat16((int)qx);
+  A.dc_quant[1 * nblk + bj] = sat16((int)qy);
+  A.dc_quant[2 * nblk + bj] = sat16((int)qb);
+}
+
+// closing rules of AdjustQuantBlockAC once the block sums are known (oracle/jxo_coef.cc)
 template <int S>
-__device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int c, float scale, float qm_mul, int quant,
-                            float thr[4], int gl) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int W = R > C ? R : C, H = R > C ? C : R, xs = W / 8, ys = H / 8;
-  if constexpr (S == kStratDCT4X4 || S == kStratDCT4X8 || S == kStratDCT8X4) return quant;
-  const float qac = scale * (float)quant;
-  if (xs > 1 || ys > 1) {
+__device__ __forceinline__ int adjust_close(int c, int quant, int ncov, float sum_hf_rc, float sum_err, float sum_vals, const float hfNZ[4],
+                                            const float hfME[4], float thr[4]) {
+  if (c == 1 && sum_vals * 8 < (float)ncov) {
+    const double kLimit = 0.46, kMul = 0.9999;
+    const int orig = quant;
+    int nq = quant;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      thr[i] -= clamp1(0.003f * (float)(xs * ys), 0.f, (c > 0 ? 0.08f : 0.12f));
-      if (thr[i] < 0.54f) thr[i] = 0.54f;
-    }
-  }
-  float r_hf = 0.0f, r_err = 0.0f, r_vals = 0.0f, nzA = 0.0f, nzB = 0.0f, meA = 0.0f, meB = 0.0f;
-  if (gl < H) {
-    const int y = gl;
-    const int yfix = y >= H / 2 ? 2 : 0;
-    // (weights are read as 16-byte vectors: rows are 32-byte aligned; a quarter of the global-load instructions)
-#pragma unroll 2
-    for (int x4 = 0; x4 < W; x4 += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(qm + y * W + x4));
-      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-      const int x = x4 + e;
-      if (x < xs && y < ys) continue;
-      const int hfix = yfix + (x >= W / 2 ? 1 : 0);
-      const float val = coef[y * kTPitch + x] * (wv[e] * qac * qm_mul);
-      const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
-      const float err = fabsf(val - v);
-      r_err += err;
-      r_vals += fabsf(v);
-      if (c == 1 && v == 0.0f) { if (x >= W / 2) { if (meB < err) meB = err; } else { if (meA < err) meA = err; } }
-      if (v != 0.0f) {
-        if (x >= W / 2) nzB += fabsf(v); else nzA += fabsf(v);
-        const bool in_corner = y >= 7 * ys && x >= 7 * xs;
-        const bool on_border = y == H - 1 || x == W - 1;
-        const bool in_larger_corner = x >= 4 * xs && y >= 4 * ys;
-        if (in_corner || (on_border && in_larger_corner)) r_hf += fabsf(val);
-      }
-      }
-    }
-  }
-  const bool top = gl < H / 2;
-  const float sum_hf_rc = group_sum<H>(r_hf), sum_err = group_sum<H>(r_err), sum_vals = group_sum<H>(r_vals);
-  float hfNZ[4];
-  hfNZ[0] = group_sum<H>(top ? nzA : 0.0f);
-  hfNZ[1] = group_sum<H>(top ? nzB : 0.0f);
-  hfNZ[2] = group_sum<H>(top ? 0.0f : nzA);
-  hfNZ[3] = group_sum<H>(top ? 0.0f : nzB);
-  if (c == 1) {
-    float hfME[4];
-    float m0 = top ? meA : 0.0f, m1 = top ? meB : 0.0f, m2 = top ? 0.0f : meA, m3 = top ? 0.0f : meB;
-#pragma unroll
-    for (int st = H / 2; st >= 1; st >>= 1) {
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, st)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, st));
-      m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, st)); m3 = fmaxf(m3, __shfl_xor_sync(0xffffffffu, m3, st));
-    }
-    hfME[0] = m0; hfME[1] = m1; hfME[2] = m2; hfME[3] = m3;
-    if (sum_vals * 8 < (float)(xs * ys)) {
-      const double kLimit = 0.46, kMul = 0.9999;
-      const int orig = quant;
-      int nq = quant;
-#pragma unroll
-      for (int i = 1; i < 4; ++i) if (nq == orig && hfNZ[i] == 0.0f && (double)hfME[i] > kLimit) nq = orig + 1;
-      quant = nq;
-      if (hfNZ[3] == 0.0f && (double)hfME[3] > kLimit) {
-        thr[3] = (float)(kMul * (double)hfME[3] * (double)nq / (double)orig);
-      } else if ((hfNZ[1] == 0.0f && (double)hfME[1] > kLimit) || (hfNZ[2] == 0.0f && (double)hfME[2] > kLimit)) {
-        const float m = hfME[1] > hfME[2] ? hfME[1] : hfME[2];
-        thr[1] = (float)(kMul * (double)m * (double)nq / (double)orig);
-        thr[2] = thr[1];
-      } else if (hfNZ[0] == 0.0f && (double)hfME[0] > kLimit) {
-        thr[0] = (float)(kMul * (double)hfME[0] * (double)nq / (double)orig);
-      }
+    for (int i = 1; i < 4; ++i) if (nq == orig && hfNZ[i] == 0.0f && (double)hfME[i] > kLimit) nq = orig + 1;
+    quant = nq;
+    if (hfNZ[3] == 0.0f && (double)hfME[3] > kLimit) {
+      thr[3] = (float)(kMul * (double)hfME[3] * (double)nq / (double)orig);
+    } else if ((hfNZ[1] == 0.0f && (double)hfME[1] > kLimit) || (hfNZ[2] == 0.0f && (double)hfME[2] > kLimit)) {
+      const float m = hfME[1] > hfME[2] ? hfME[1] : hfME[2];
+      thr[1] = (float)(kMul * (double)m * (double)nq / (double)orig);
+      thr[2] = thr[1];
+    } else if (hfNZ[0] == 0.0f && (double)hfME[0] > kLimit) {
+      thr[0] = (float)(kMul * (double)hfME[0] * (double)nq / (double)orig);
     }
   }
   {
@@ -130,9 +124,7 @@ __device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int
   if constexpr (S == kStratDCT) {
     if (hfNZ[0] + hfNZ[1] + hfNZ[2] + hfNZ[3] < 11) { quant += 1; if (quant >= 256) quant = 255; }
   }
-  if constexpr (S == kStratDCT16X16 || S == kStratDCT32X32 || S == kStratDCT32X16 || S == kStratDCT16X32 ||
-                S == kStratDCT16X8 || S == kStratDCT8X16) {
-    // (oracle: strategy >= DCT16X16, i.e. every multi-block transform of the emitted set)
+  if constexpr (S >= kStratDCT16X16 && S != kStratDCT4X8 && S != kStratDCT8X4) {
     const double kMul1[4][3] = {{0.22080615753848404, 0.45797479824262011, 0.29859235095977965},
                                 {0.70109486510286834, 0.16185281305512639, 0.14387691730035473},
                                 {0.114985964456218638, 0.44656840441027695, 0.10587658215149048},
@@ -144,11 +136,8 @@ __device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int
     const double kQuantNormalizer = 2.2942708343284721;
     const double se = (double)sum_err * kQuantNormalizer;
     const double sv = (double)sum_vals * kQuantNormalizer;
-    int ix = 3;
-    if (S == kStratDCT32X16 || S == kStratDCT16X32) ix = 1;
-    else if (S == kStratDCT16X16) ix = 0;
-    else if (S == kStratDCT32X32) ix = 2;
-    const double lim = kMul1[ix][c] * (double)(xs * ys * 64) + kMul2[ix][c] * sv;
+    constexpr int ix = (S == kStratDCT32X16 || S == kStratDCT16X32) ? 1 : (S == kStratDCT16X16 ? 0 : (S == kStratDCT32X32 ? 2 : 3));
+    const double lim = kMul1[ix][c] * (double)(ncov * 64) + kMul2[ix][c] * sv;
     int step = (int)(se / lim);
     if (step >= 2) step = 2;
     if (step < 0) step = 0;
@@ -157,427 +146,533 @@ __device__ int adjust_quant(const float* coef, const float* __restrict__ qm, int
   return quant;
 }
 
-// oracle QuantizeBlockAC for row gl; quantised ints are written to `out` (same [H][kTPitch] layout, int bits)
-template <int S>
-__device__ __forceinline__ void quantize_rows(const float* coef, const float* __restrict__ qm, int c, float qac_mul, float thr[4],
-                                              int* out, int gl) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int W = R > C ? R : C, H = R > C ? C : R, xs = W / 8, ys = H / 8;
-  if (c != 1 && xs * ys >= 4) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { thr[i] -= 0.00744f * (float)(xs * ys); if (thr[i] < 0.5f) thr[i] = 0.5f; }
+// ====================================================================================================== 8x8 strategies
+// natural (zig-zag) coefficient order of an 8x8 block (oracle NaturalCoeffOrder, cx = cy = 1), at compile time
+struct Zigzag8 { int pos[64]; };
+constexpr Zigzag8 make_zigzag8() {
+  Zigzag8 z{};
+  int cur = 1;
+  for (int i = 0; i < 8; ++i)
+    for (int j = 0; j <= i; ++j) {
+      int x = j, y = i - j;
+      if (i % 2) { const int t = x; x = y; y = t; }
+      const int val = (x < 1 && y < 1) ? 0 : cur++;
+      z.pos[val] = y * 8 + x;
+    }
+  for (int ip = 7; ip > 0; --ip) {
+    const int i = ip - 1;
+    for (int j = 0; j <= i; ++j) {
+      int x = 7 - (i - j), y = 7 - j;
+      if (i % 2) { const int t = x; x = y; y = t; }
+      z.pos[cur++] = y * 8 + x;
+    }
   }
-  if (gl < H) {
-    const int y = gl, yfix = (y >= H / 2) ? 2 : 0;
-#pragma unroll 2
-    for (int x4 = 0; x4 < W; x4 += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(qm + y * W + x4));
-      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+  return z;
+}
+__device__ constexpr Zigzag8 kZigzag8 = make_zigzag8();
+
+// oracle QuantizeBlockAC for an 8x8 block in registers; returns the values in place (as ints)
+__device__ __forceinline__ void quantize8(const float* cf, const float* __restrict__ qm, float qac_mul, const float thr[4], int* out) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int x = x4 + e;
-        const float t = thr[yfix + (x >= W / 2 ? 1 : 0)];
-        const float q = wv[e] * qac_mul;
-        const float val = q * coef[y * kTPitch + x];
-        int v = (fabsf(val) >= t) ? (int)rintf(val) : 0;
-        if (x < xs && y < ys) v = 0;
-        v = v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
-        out[y * kTPitch + x] = v;
+  for (int k = 0; k < 64; ++k) {
+    const int y = k >> 3, x = k & 7;
+    const float t = thr[(y >= 4 ? 2 : 0) + (x >= 4 ? 1 : 0)];
+    const float q = __ldg(qm + k) * qac_mul;
+    const float val = q * cf[k];
+    int v = (fabsf(val) >= t) ? (int)rintf(val) : 0;
+    if (k == 0) v = 0;
+    v = v > 32767 ? 32767 : (v < -32767 ? -32767 : v);
+    out[k] = v;
+  }
+}
+
+// scan-order output of one channel of an 8x8 block + its non-zero statistics
+__device__ __forceinline__ void emit8(const CoeffArgs& A, const int* q, size_t cblk, int slot, int c, size_t bi, size_t nblk) {
+  int nz = 0, last = 0;
+  uint32_t words[32];
+#pragma unroll
+  for (int k = 0; k < 64; k += 2) {
+    const int a = q[kZigzag8.pos[k]], b = q[kZigzag8.pos[k + 1]];
+    if (a != 0) { ++nz; last = k; }
+    if (b != 0) { ++nz; last = k + 1; }
+    words[k >> 1] = ((uint32_t)a & 0xFFFFu) | ((uint32_t)b << 16);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(A.coeffs + (cblk * 3 + slot) * 64);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = make_uint4(words[4 * i], words[4 * i + 1], words[4 * i + 2], words[4 * i + 3]);
+  A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nz;
+  A.lastk[(size_t)c * nblk + bi] = (uint16_t)last;
+  A.nzeros[(size_t)c * nblk + bi] = (uint8_t)nz;
+}
+
+__device__ __forceinline__ void load_block8(const float* __restrict__ plane, int pitch, int bx, int by, float* p) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float4* src = reinterpret_cast<const float4*>(plane + (size_t)(by * 8 + r) * pitch + bx * 8);
+    const float4 a = __ldg(src), d = __ldg(src + 1);
+    p[r * 8 + 0] = a.x; p[r * 8 + 1] = a.y; p[r * 8 + 2] = a.z; p[r * 8 + 3] = a.w;
+    p[r * 8 + 4] = d.x; p[r * 8 + 5] = d.y; p[r * 8 + 6] = d.z; p[r * 8 + 7] = d.w;
+  }
+}
+
+// oracle AdjustQuantBlockAC for the plain 8x8 DCT (the other 8x8 strategies are not adjusted): lane = storage row
+__device__ __forceinline__ int adjust_quant8(const float* cf, const float* __restrict__ qm, int c, float scale, float qm_mul, int quant, float thr[4]) {
+  const float qac = scale * (float)quant;
+  float r_hf[8], r_err[8], r_vals[8], nz0[8], nz1[8], nz2[8], nz3[8];
+  float hfME[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int y = 0; y < 8; ++y) {
+    float a_hf = 0.0f, a_err = 0.0f, a_vals = 0.0f, a_nzA = 0.0f, a_nzB = 0.0f;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      if (x == 0 && y == 0) continue;
+      const int k = y * 8 + x;
+      const int hfix = (y >= 4 ? 2 : 0) + (x >= 4 ? 1 : 0);
+      const float val = cf[k] * (__ldg(qm + k) * qac * qm_mul);
+      const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
+      const float err = fabsf(val - v);
+      a_err += err;
+      a_vals += fabsf(v);
+      if (c == 1 && v == 0.0f) { if (hfME[hfix] < err) hfME[hfix] = err; }
+      if (v != 0.0f) {
+        if (x >= 4) a_nzB += fabsf(v); else a_nzA += fabsf(v);
+        const bool in_corner = y >= 7 && x >= 7;
+        const bool on_border = y == 7 || x == 7;
+        const bool in_larger_corner = x >= 4 && y >= 4;
+        if (in_corner || (on_border && in_larger_corner)) a_hf += fabsf(val);
       }
     }
+    r_hf[y] = a_hf; r_err[y] = a_err; r_vals[y] = a_vals;
+    nz0[y] = y < 4 ? a_nzA : 0.0f; nz1[y] = y < 4 ? a_nzB : 0.0f; nz2[y] = y < 4 ? 0.0f : a_nzA; nz3[y] = y < 4 ? 0.0f : a_nzB;
   }
+  const float hfNZ[4] = {tree8(nz0), tree8(nz1), tree8(nz2), tree8(nz3)};
+  return adjust_close<kStratDCT>(c, quant, 1, tree8(r_hf), tree8(r_err), tree8(r_vals), hfNZ, hfME, thr);
 }
 
-__device__ __forceinline__ float resample_scale(int n_from, int n_to, int k) {
-  if (n_to == 1) return 1.0f;
-  if (n_from == 16) return k == 0 ? 1.e+00f : 9.017642e-01f;
-  return k == 0 ? 1.e+00f : (k == 1 ? 9.7488683e-01f : (k == 2 ? 9.017642e-01f : 7.870549e-01f));
-}
-
-template <int N> __device__ __forceinline__ void idct_small(float* v) { idct1d<N>(v); }
-
-// oracle DcFromLowestFrequencies: dc[cy][cx] from the cy x cx lowest frequencies (serial, tiny)
 template <int S>
-__device__ void dc_from_llf(const float* coef, float* dc /*[cy*cx]*/) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C, cy = R / 8, cx = C / 8;
-  if constexpr (cx == 1 && cy == 1) { dc[0] = coef[0]; return; }
-  else {
-    float llf[16], t[16];
-#pragma unroll
-    for (int vf = 0; vf < cy; ++vf)
-#pragma unroll
-      for (int hf = 0; hf < cx; ++hf) {
-        const float cv = (R >= C) ? coef[hf * kTPitch + vf] : coef[vf * kTPitch + hf];
-        llf[vf * cx + hf] = cv * resample_scale(R, cy, vf) * resample_scale(C, cx, hf);
-      }
-#pragma unroll
-    for (int hf = 0; hf < cx; ++hf) {
-      float v[cy];
-#pragma unroll
-      for (int y = 0; y < cy; ++y) v[y] = llf[y * cx + hf];
-      idct1d<cy>(v);
-#pragma unroll
-      for (int y = 0; y < cy; ++y) t[y * cx + hf] = v[y];
-    }
-#pragma unroll
-    for (int y = 0; y < cy; ++y) {
-      float v[cx];
-#pragma unroll
-      for (int x = 0; x < cx; ++x) v[x] = t[y * cx + x];
-      idct1d<cx>(v);
-#pragma unroll
-      for (int x = 0; x < cx; ++x) dc[y * cx + x] = v[x];
-    }
-  }
-}
-
-struct CoeffArgs {
-  FrameDim fd;
-  const QuantDev* qd;
-  AcsTables T;                      // weights / dequant per quant-table kind
-  const uint16_t* inv_order[13];    // per order class: coefficient position -> scan index
-  const int8_t* cmap;
-  float x_qm_mul, b_qm_mul;
-  int adjust;
-  int32_t* raw_qf;
-  int16_t* coeffs;
-  int16_t* dc_quant;
-  uint8_t* nzeros;
-  uint16_t* nzcount;
-  uint16_t* lastk;
-};
-
-// One lane group (GS = max(R, C) lanes) per transform, 32 / GS transforms side by side in a warp.
-// Inactive groups run the same instruction stream on the tile origin with every store suppressed.
-template <int S>
-__device__ void process_transform(CoeffShared& sh, int warp, bool active, int ox, int oy, int bx, int by, const CoeffArgs& A,
-                                  int kind, int order_class, int lane) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int W = R > C ? R : C, H = R > C ? C : R, cxb = C / 8, cyb = R / 8, n = cxb * cyb, size = R * C;
-  constexpr int GS = W;                                    // lanes per transform
+__global__ void __launch_bounds__(64) k_coeff8(CoeffArgs A) {
   const FrameDim& fd = A.fd;
-  const int gl = lane & (GS - 1), gbase = lane & ~(GS - 1), go = (lane / GS) * GS * kTPitch;
-  // (every templated helper below has ONE call site inside a non-unrolled channel loop: the kernel holds ten
-  // strategy instantiations and instruction-cache misses were 29 % of its stalls when each helper was inlined 3x)
-  float* bufs[3] = {sh.buf[warp][0] + go, sh.buf[warp][1] + go, sh.buf[warp][2] + go};
-  const int po = oy * kTPitch + ox;
-#pragma unroll 1
-  for (int c = 0; c < 3; ++c) fwd_transform<S>(sh.px[c] + po, kTPitch, bufs[c], bufs[c], gl);
-  float* b0 = bufs[0]; float* b1 = bufs[1]; float* b2 = bufs[2];
+  const unsigned n = *A.count;
+  const unsigned i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= n) return;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
-  const size_t bi = (size_t)by * fd.bxs + bx;
+  const size_t bi = A.list[i];
+  const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
   const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
-  // ---- DC of every covered block (AddVarDCTDC quantisation: Y first, B with the 1.0 base correlation)
-  if (gl == 0 && active) {
-    float dc[3][16];
-#pragma unroll 1
-    for (int c = 0; c < 3; ++c) dc_from_llf<S>(bufs[c], dc[c]);
-    const int quant_dc = A.qd->quant_dc;
-    const float gsq = scale * (float)quant_dc;
-    const float inv_quant_dc = inv_gs / (float)quant_dc;
-    const float y_factor = inv_quant_dc * (1.0f / 512.0f);
-    for (int j = 0; j < n; ++j) {
-      const size_t bj = bi + (size_t)(j / cxb) * fd.bxs + (j % cxb);
-      const float qy = roundf(dc[1][j] * (512.0f * gsq));
-      const float qx = roundf((dc[0][j] - qy * (y_factor * 0.0f)) * (4096.0f * gsq));
-      const float qb = roundf((dc[2][j] - qy * (y_factor * 1.0f)) * (256.0f * gsq));
-      const int iy = (int)qy, ix = (int)qx, ib = (int)qb;
-      A.dc_quant[0 * nblk + bj] = (int16_t)(ix > 32767 ? 32767 : (ix < -32768 ? -32768 : ix));
-      A.dc_quant[1 * nblk + bj] = (int16_t)(iy > 32767 ? 32767 : (iy < -32768 ? -32768 : iy));
-      A.dc_quant[2 * nblk + bj] = (int16_t)(ib > 32767 ? 32767 : (ib < -32768 ? -32768 : ib));
-    }
-  }
-  // ---- quant adjust (channel order Y, X, B; the result is the maximum, Y's thresholds are kept)
-  const float* qm = A.T.w[kind];
-  const float* dq = A.T.dq[kind];
-  int quant = active ? A.raw_qf[bi] : 1;
+  const int orig = A.raw_qf[bi];
+  const float* planes[3] = {A.X, A.Y, A.B};
+  float ycoef[64];
+  float dc[3];
+  int quant = orig;
   float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-  if (A.adjust) {
-    const int orig = quant;
+  // ---- pass A: transforms, DC, quant adjust (channel order Y, X, B; the result is the maximum over the channels)
+  {
     int maxq = 0;
 #pragma unroll 1
     for (int it = 0; it < 3; ++it) {
       const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
-      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
-      maxq = max(maxq, adjust_quant<S>(bufs[c], qm + c * size, c, scale, mulc, orig, thr, gl));
-      if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
+      float p[64], cf[64];
+      load_block8(planes[c], fd.pitch, bx, by, p);
+      fwd8x8<S>(p, cf);
+      dc[c] = cf[0];
+      if (it == 0) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) ycoef[k] = cf[k];
+      }
+      if (S == kStratDCT && A.adjust) {
+        float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+        const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+        maxq = max(maxq, adjust_quant8(cf, A.w + c * 64, c, scale, mulc, orig, thr));
+        if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
+      }
     }
-    quant = __shfl_sync(0xffffffffu, maxq, gbase);
-    thr_y[0] = __shfl_sync(0xffffffffu, thr_y[0], gbase); thr_y[1] = __shfl_sync(0xffffffffu, thr_y[1], gbase);
-    thr_y[2] = __shfl_sync(0xffffffffu, thr_y[2], gbase); thr_y[3] = __shfl_sync(0xffffffffu, thr_y[3], gbase);
-  } else {
-    thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f;
+    if (A.adjust) { if (S == kStratDCT) quant = maxq; }
+    else { thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f; }
   }
-  // ---- quantise Y in place, roundtrip, remove chroma-from-luma, quantise X and B in place (all row-local)
+  store_dc(A, bi, dc[0], dc[1], dc[2]);
+  A.raw_qf[bi] = quant;
+  // ---- pass B: quantise Y, roundtrip it, remove the chroma-from-luma share from X and B, quantise them
   const float qac = scale * (float)quant;
-  const int* qy = reinterpret_cast<const int*>(b1);
   const float inv_qac = inv_gs / (float)quant;
+  const int g = (by >> 5) * fd.gxs + (bx >> 5);
+  const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(by & 31) * 32 + (bx & 31);
   const int tx = bx >> 3, ty = by >> 3;
   const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
   const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
-#pragma unroll 1
-  for (int it = 0; it < 3; ++it) {
-    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
-    if (it == 1 && gl < H) {
-#pragma unroll 2
-      for (int x4 = 0; x4 < W; x4 += 4) {
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dq + size + gl * W + x4));
-        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+  int qy[64];
+  quantize8(ycoef, A.w + 64, qac * 1.0f, thr_y, qy);
+  emit8(A, qy, cblk, 0, 1, bi, nblk);
+  // dequantised Y replaces the coefficients (only its products with the two factors are needed below)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int x = x4 + e;
-          const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dv[e]) * inv_qac;
-          b0[gl * kTPitch + x] = __fmaf_rn(-x_factor, yrt, b0[gl * kTPitch + x]);
-          b2[gl * kTPitch + x] = __fmaf_rn(-b_factor, yrt, b2[gl * kTPitch + x]);
-        }
-      }
-    }
-    float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-    if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
-    const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
-    quantize_rows<S>(bufs[c], qm + c * size, c, qac * mulc, thr, reinterpret_cast<int*>(bufs[c]), gl);
-  }
-  // ---- scan-order output + non-zero statistics
-  const uint16_t* inv = A.inv_order[order_class];
-  constexpr int log2n = n == 1 ? 0 : (n == 2 ? 1 : (n == 4 ? 2 : (n == 8 ? 3 : 4)));
+  for (int k = 0; k < 64; ++k) ycoef[k] = (quant_bias(1, qy[k]) * __ldg(A.dq + 64 + k)) * inv_qac;
 #pragma unroll 1
-  for (int slot = 0; slot < 3; ++slot) {
-    const int c = slot == 0 ? 1 : (slot == 1 ? 0 : 2);
-    const int* src = reinterpret_cast<const int*>(bufs[c]);
-    int nz = 0, last = 0;
-    uint2 inv4 = make_uint2(0u, 0u);
-    if (gl < H && active) {
-      for (int x = 0; x < W; ++x) {
-        const int v = src[gl * kTPitch + x];
-        // (scan indices of four positions per 8-byte load)
-        if ((x & 3) == 0) inv4 = __ldg(reinterpret_cast<const uint2*>(inv + gl * W + x));
-        const int k = (int)(((x & 2) ? inv4.y : inv4.x) >> ((x & 1) * 16)) & 0xFFFF;
-        const int j = k >> 6;
-        const int cbx = bx + (j % cxb), cby = by + (j / cxb);
-        const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
-        const size_t blk = (size_t)g * kGroupBlocks + (size_t)(cby & 31) * 32 + (cbx & 31);
-        A.coeffs[(blk * 3 + slot) * 64 + (k & 63)] = (int16_t)v;
-        if (v != 0) { ++nz; last = max(last, k); }
-      }
-    }
-    nz = group_isum<H>(nz);
+  for (int it = 0; it < 2; ++it) {
+    const int c = it == 0 ? 0 : 2;
+    const float factor = c == 0 ? x_factor : b_factor;
+    float p[64], cf[64];
+    load_block8(planes[c], fd.pitch, bx, by, p);
+    fwd8x8<S>(p, cf);
 #pragma unroll
-    for (int st = H / 2; st >= 1; st >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, st));
-    if (gl == 0 && active) {
-      const int shared = (nz + n - 1) >> log2n;
-      A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nz;
-      A.lastk[(size_t)c * nblk + bi] = (uint16_t)last;
-      for (int j = 0; j < n; ++j) A.nzeros[(size_t)c * nblk + bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = (uint8_t)shared;
-    }
+    for (int k = 0; k < 64; ++k) cf[k] = __fmaf_rn(-factor, ycoef[k], cf[k]);
+    const float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+    int q[64];
+    quantize8(cf, A.w + c * 64, qac * (c == 0 ? A.x_qm_mul : A.b_qm_mul), thr, q);
+    emit8(A, q, cblk, c == 0 ? 1 : 2, c, bi, nblk);
   }
-  if (gl == 0 && active) for (int j = 0; j < n; ++j) A.raw_qf[bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = quant;
-  __syncwarp();
 }
 
-// Channel-parallel form for the 32-lane transforms (32x32, 32x16, 16x32): such a transform fills a warp, a 32x32 square
-// holds one or two of them, and with one warp per transform the other warps of the CTA had nothing to do (ncu: 6.5 %
-// active warps, 12 % issue utilisation, a 32x32 transform took 160 k cycles).  Here warps 0..2 take channels X, Y, B of the
-// SAME transform and meet at CTA barriers where the channels depend on each other (the adjusted quant is the maximum
-// over the channels; X and B need the quantised Y); warp 3 quantises the DC values and writes the per-block side data.
-// Every per-channel step is the code of process_transform, so the results are bit-identical.  Called by all warps.
-template <int S>
-__device__ void process_transform_cp(CoeffShared& sh, int warp, int ox, int oy, int bx, int by, const CoeffArgs& A, int kind,
-                                     int order_class, int lane) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int W = R > C ? R : C, H = R > C ? C : R, cxb = C / 8, cyb = R / 8, n = cxb * cyb, size = R * C;
-  static_assert(W == 32, "channel-parallel path is for 32-lane transforms");
-  const FrameDim& fd = A.fd;
-  const int gl = lane;
-  const int c = warp;                                   // 0 = X, 1 = Y, 2 = B, 3 = helper
-  float* buf = sh.buf[warp][0];                         // this warp's coefficient rows
-  const int* qy = reinterpret_cast<const int*>(sh.buf[1][0]);
-  const int po = oy * kTPitch + ox;
-  const size_t nblk = (size_t)fd.bxs * fd.bys;
-  const size_t bi = (size_t)by * fd.bxs + bx;
-  const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
-  const float* qm = A.T.w[kind];
-  const float* dq = A.T.dq[kind];
-  const int orig = A.raw_qf[bi];
-  const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
-  // ---- phase 1: transform + quant adjust of the warp's channel
-  if (c < 3) {
-    fwd_transform<S>(sh.px[c] + po, kTPitch, buf, buf, gl);
-    if (gl == 0) dc_from_llf<S>(buf, sh.cp_dc[c]);
-    if (A.adjust) {
-      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      const int q = adjust_quant<S>(buf, qm + c * size, c, scale, mulc, orig, thr, gl);
-      if (gl == 0) {
-        sh.cp_q[c] = q;
-        if (c == 1) { sh.cp_thr[0] = thr[0]; sh.cp_thr[1] = thr[1]; sh.cp_thr[2] = thr[2]; sh.cp_thr[3] = thr[3]; }
-      }
-    }
+// ====================================================================================================== 16 / 32 / 64
+// Lane geometry of a transform inside the N x N square (SquareXform modes): square = N lanes x N values; tall = the
+// first N/2 lanes x N values (left half; the right half of the square is not loaded); wide = N lanes x the first N/2
+// values (top half).  (x, y) below are storage coordinates (long side horizontal): square / tall: y = lane, x = j;
+// wide: x = lane, y = j.
+template <int N, int MODE> struct CoeffGeom {
+  static constexpr int H = N / 2;
+  static constexpr int W = N;                                   // storage width (long side)
+  static constexpr int HS = MODE == kModeSq ? N : H;            // storage height
+  static constexpr int LANES = MODE == kModeTall2 ? H : N;      // lanes that own coefficients
+  static constexpr int VALS = MODE == kModeWide2 ? H : N;       // values per lane
+  static constexpr int R = MODE == kModeWide2 ? H : N, C = MODE == kModeTall2 ? H : N;   // pixel rows / columns
+  static constexpr int cxb = C / 8, cyb = R / 8, ncov = cxb * cyb, xs = W / 8, ys = HS / 8;
+  static constexpr int S = N == 16 ? (MODE == kModeSq ? kStratDCT16X16 : MODE == kModeTall2 ? kStratDCT16X8 : kStratDCT8X16)
+                         : N == 32 ? (MODE == kModeSq ? kStratDCT32X32 : MODE == kModeTall2 ? kStratDCT32X16 : kStratDCT16X32)
+                                   : (MODE == kModeSq ? kStratDCT64X64 : MODE == kModeTall2 ? kStratDCT64X32 : kStratDCT32X64);
+};
+
+// sums / maxima over the LANES lanes that own coefficients (N = 64 square / wide: two warps through `xch`)
+template <int N, int LANES, int K>
+__device__ __forceinline__ void lane_sums(float (&v)[K], float* xch, int l, int bar_id) {
+  if constexpr (LANES == 64) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) xch[k * 64 + l] = v[k];
+    SquareXform<N>::sync(bar_id);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = v[k] + xch[k * 64 + (l ^ 32)];
+    SquareXform<N>::sync(bar_id);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = group_sum<32>(v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = group_sum<LANES>(v[k]);
   }
-  __syncthreads();
-  int quant = orig;
-  float thr_y[4] = {0.56f, 0.62f, 0.62f, 0.62f};
-  if (A.adjust) {
-    quant = max(sh.cp_q[1], max(sh.cp_q[0], sh.cp_q[2]));
-    thr_y[0] = sh.cp_thr[0]; thr_y[1] = sh.cp_thr[1]; thr_y[2] = sh.cp_thr[2]; thr_y[3] = sh.cp_thr[3];
+}
+template <int N, int LANES, int K>
+__device__ __forceinline__ void lane_maxs(float (&v)[K], float* xch, int l, int bar_id) {
+  if constexpr (LANES == 64) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) xch[k * 64 + l] = v[k];
+    SquareXform<N>::sync(bar_id);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = fmaxf(v[k], xch[k * 64 + (l ^ 32)]);
+    SquareXform<N>::sync(bar_id);
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = group_fmax<32>(v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = group_fmax<LANES>(v[k]);
   }
+}
+
+// oracle AdjustQuantBlockAC for a lane group; u = the lane's coefficients, wrow = its row of the lane-ordered table
+template <int N, int MODE>
+__device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __restrict__ wrow, int c, float scale, float qm_mul, int quant,
+                                               float thr[4], int l, bool owner, float* xch, int bar_id) {
+  using G = CoeffGeom<N, MODE>;
   const float qac = scale * (float)quant;
-  const float inv_qac = inv_gs / (float)quant;
-  // ---- phase 2: Y quantised in place; the helper warp does the DC values and the integer quant field meanwhile
-  if (c == 1) quantize_rows<S>(buf, qm + size, 1, qac * 1.0f, thr_y, reinterpret_cast<int*>(buf), gl);
-  if (c == 3 && gl == 0) {
-    const int quant_dc = A.qd->quant_dc;
-    const float gsq = scale * (float)quant_dc;
-    const float inv_quant_dc = inv_gs / (float)quant_dc;
-    const float y_factor = inv_quant_dc * (1.0f / 512.0f);
-    for (int j = 0; j < n; ++j) {
-      const size_t bj = bi + (size_t)(j / cxb) * fd.bxs + (j % cxb);
-      const float fy = roundf(sh.cp_dc[1][j] * (512.0f * gsq));
-      const float fx = roundf((sh.cp_dc[0][j] - fy * (y_factor * 0.0f)) * (4096.0f * gsq));
-      const float fb = roundf((sh.cp_dc[2][j] - fy * (y_factor * 1.0f)) * (256.0f * gsq));
-      const int iy = (int)fy, ix = (int)fx, ib = (int)fb;
-      A.dc_quant[0 * nblk + bj] = (int16_t)(ix > 32767 ? 32767 : (ix < -32768 ? -32768 : ix));
-      A.dc_quant[1 * nblk + bj] = (int16_t)(iy > 32767 ? 32767 : (iy < -32768 ? -32768 : iy));
-      A.dc_quant[2 * nblk + bj] = (int16_t)(ib > 32767 ? 32767 : (ib < -32768 ? -32768 : ib));
-      A.raw_qf[bj] = quant;
-    }
-  }
-  __syncthreads();
-  // ---- phase 3: X and B remove their chroma-from-luma share of the dequantised Y and quantise; every channel goes out
-  if (c == 0 || c == 2) {
-    const int tx = bx >> 3, ty = by >> 3;
-    const float factor = c == 0 ? 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f
-                                : 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
-    if (gl < H) {
-#pragma unroll 2
-      for (int x4 = 0; x4 < W; x4 += 4) {
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(dq + size + gl * W + x4));
-        const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int x = x4 + e;
-          const float yrt = (quant_bias(1, qy[gl * kTPitch + x]) * dv[e]) * inv_qac;
-          buf[gl * kTPitch + x] = __fmaf_rn(-factor, yrt, buf[gl * kTPitch + x]);
+  for (int i = 0; i < 4; ++i) {
+    thr[i] -= clamp1(0.003f * (float)(G::xs * G::ys), 0.f, (c > 0 ? 0.08f : 0.12f));
+    if (thr[i] < 0.54f) thr[i] = 0.54f;
+  }
+  float r_hf = 0.0f, r_err = 0.0f, r_vals = 0.0f, nzA = 0.0f, nzB = 0.0f, meA = 0.0f, meB = 0.0f;
+  if (owner) {
+#pragma unroll
+    for (int j4 = 0; j4 < G::VALS; j4 += 4) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j4));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j4 + e;
+        const int x = MODE == kModeWide2 ? l : j, y = MODE == kModeWide2 ? j : l;
+        if (x < G::xs && y < G::ys) continue;
+        const int hfix = (y >= G::HS / 2 ? 2 : 0) + (x >= G::W / 2 ? 1 : 0);
+        const float val = u[j] * (wv[e] * qac * qm_mul);
+        const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
+        const float err = fabsf(val - v);
+        r_err += err;
+        r_vals += fabsf(v);
+        // the half that varies along the lane's own values: x for square / tall lanes, y for wide lanes
+        const bool second = MODE == kModeWide2 ? (y >= G::HS / 2) : (x >= G::W / 2);
+        if (c == 1 && v == 0.0f) { if (second) { if (meB < err) meB = err; } else { if (meA < err) meA = err; } }
+        if (v != 0.0f) {
+          if (second) nzB += fabsf(v); else nzA += fabsf(v);
+          const bool in_corner = y >= 7 * G::ys && x >= 7 * G::xs;
+          const bool on_border = y == G::HS - 1 || x == G::W - 1;
+          const bool in_larger_corner = x >= 4 * G::xs && y >= 4 * G::ys;
+          if (in_corner || (on_border && in_larger_corner)) r_hf += fabsf(val);
         }
       }
     }
-    float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-    quantize_rows<S>(buf, qm + c * size, c, qac * mulc, thr, reinterpret_cast<int*>(buf), gl);
   }
-  if (c < 3) {
-    const uint16_t* inv = A.inv_order[order_class];
-    constexpr int log2n = n == 1 ? 0 : (n == 2 ? 1 : (n == 4 ? 2 : (n == 8 ? 3 : 4)));
-    const int slot = c == 1 ? 0 : (c == 0 ? 1 : 2);
-    const int* src = reinterpret_cast<const int*>(buf);
-    int nz = 0, last = 0;
-    uint2 inv4 = make_uint2(0u, 0u);
-    if (gl < H) {
-      for (int x = 0; x < W; ++x) {
-        const int v = src[gl * kTPitch + x];
-        // (scan indices of four positions per 8-byte load)
-        if ((x & 3) == 0) inv4 = __ldg(reinterpret_cast<const uint2*>(inv + gl * W + x));
-        const int k = (int)(((x & 2) ? inv4.y : inv4.x) >> ((x & 1) * 16)) & 0xFFFF;
-        const int j = k >> 6;
-        const int cbx = bx + (j % cxb), cby = by + (j / cxb);
-        const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
-        const size_t blk = (size_t)g * kGroupBlocks + (size_t)(cby & 31) * 32 + (cbx & 31);
-        A.coeffs[(blk * 3 + slot) * 64 + (k & 63)] = (int16_t)v;
-        if (v != 0) { ++nz; last = max(last, k); }
+  // quadrant index hfix = (y half) * 2 + (x half); `first` = the lane sits in the first half of the lane-indexed axis
+  const bool first = MODE == kModeWide2 ? (l < G::W / 2) : (l < G::HS / 2);
+  float s[7];
+  s[0] = r_hf; s[1] = r_err; s[2] = r_vals;
+  if constexpr (MODE == kModeWide2) {   // lane = x: first -> quadrants 0 (A: top) and 2 (B: bottom); else 1 and 3
+    s[3] = first ? nzA : 0.0f; s[4] = first ? 0.0f : nzA; s[5] = first ? nzB : 0.0f; s[6] = first ? 0.0f : nzB;
+  } else {                              // lane = y: first -> quadrants 0 (A: left) and 1 (B: right); else 2 and 3
+    s[3] = first ? nzA : 0.0f; s[4] = first ? nzB : 0.0f; s[5] = first ? 0.0f : nzA; s[6] = first ? 0.0f : nzB;
+  }
+  lane_sums<N, G::LANES, 7>(s, xch, l, bar_id);
+  const float hfNZ[4] = {s[3], s[4], s[5], s[6]};
+  float hfME[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (c == 1) {
+    float m[4];
+    if constexpr (MODE == kModeWide2) { m[0] = first ? meA : 0.0f; m[1] = first ? 0.0f : meA; m[2] = first ? meB : 0.0f; m[3] = first ? 0.0f : meB; }
+    else { m[0] = first ? meA : 0.0f; m[1] = first ? meB : 0.0f; m[2] = first ? 0.0f : meA; m[3] = first ? 0.0f : meB; }
+    lane_maxs<N, G::LANES, 4>(m, xch, l, bar_id);
+    hfME[0] = m[0]; hfME[1] = m[1]; hfME[2] = m[2]; hfME[3] = m[3];
+  }
+  return adjust_close<G::S>(c, quant, G::ncov, s[0], s[1], s[2], hfNZ, hfME, thr);
+}
+
+template <int N> struct CoeffSqGeom {
+  static constexpr int kGroupsPerWarp = N == 16 ? 2 : 1;
+  static constexpr int kThreads = N == 64 ? 64 : 128;
+  static constexpr int kUnits = N == 64 ? 1 : 4;
+  static constexpr int kGroups = kUnits * kGroupsPerWarp;
+  static constexpr int kSq = N == 16 ? 256 + 16 : N * N;                    // one square buffer (16: skewed)
+  static constexpr int kGroupFloats = 3 * kSq + 3 * 64 + 7 * 64;            // transposition square, X / B stash, LLF, exchange
+  static constexpr int kSmemFloats = kGroups * kGroupFloats;
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(CoeffSqGeom<N>::kThreads) k_coeffsq(CoeffArgs A) {
+  using G = CoeffGeom<N, MODE>;
+  using CG = CoeffSqGeom<N>;
+  using SX = SquareXform<N>;
+  extern __shared__ __align__(16) float smem_f[];
+  const FrameDim& fd = A.fd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int l = N == 64 ? tid : (lane & (N - 1));
+  const int grp = N == 64 ? 0 : warp * CG::kGroupsPerWarp + (N == 16 ? (lane >> 4) : 0);
+  float* base = smem_f + grp * CG::kGroupFloats;
+  float* tbuf = base; float* stash[2] = {base + CG::kSq, base + 2 * CG::kSq};
+  float* llf = base + 3 * CG::kSq;          // [c][64]
+  float* xch = llf + 3 * 64;                // [7][64]
+  const typename SX::Col col = SX::col_of(l);
+  const unsigned n = *A.count;
+  const size_t nblk = (size_t)fd.bxs * fd.bys;
+  const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
+  const bool owner = l < G::LANES;
+  constexpr int bar_id = 1;
+  for (unsigned item0 = blockIdx.x * CG::kGroups; item0 < n; item0 += gridDim.x * CG::kGroups) {
+    const unsigned item = item0 + grp;
+    const bool active = item < n;
+    const size_t bi = active ? A.list[item] : 0;
+    const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
+    const int orig = active ? A.raw_qf[bi] : 1;
+    const float* planes[3] = {A.X, A.Y, A.B};
+    const int py = by * 8 + l;
+    float uY[G::VALS];
+    float dcv[3][G::cxb];                    // lane y < cyb: DC row y of the covered blocks
+    float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+    int maxq = 0;
+    const float* wlane = A.w + (size_t)l * G::VALS;      // + c * LANES * VALS
+    // ---- pass A: per channel transform, DC from the lowest frequencies, quant adjust; X and B wait in shared memory
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+      const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+      float v[N], u[N];
+#pragma unroll
+      for (int j = 0; j < N / 4; ++j) {
+        float4 q4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        // only the transform's own R x C pixels are loaded (the rest of the square stays zero)
+        if (active && l < G::R && 4 * j < G::C) q4 = __ldg(reinterpret_cast<const float4*>(planes[c] + (size_t)py * fd.pitch + bx * 8 + 4 * j));
+        v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
+      }
+      SX::template forward<MODE>(tbuf, l, col, v, u, bar_id);
+      // lowest frequencies -> DC of the covered blocks (oracle DcFromLowestFrequencies): lane hf < cxb scales its cyb
+      // values and inverts them vertically, lane y < cyb then inverts row y horizontally
+      if (l < G::cxb) {
+        float t[G::cyb];
+#pragma unroll
+        for (int vf = 0; vf < G::cyb; ++vf) t[vf] = u[vf] * resample_scale(G::R, vf) * resample_scale(G::C, l);
+        idct1d<G::cyb>(t);
+#pragma unroll
+        for (int y = 0; y < G::cyb; ++y) llf[c * 64 + y * G::cxb + l] = t[y];
+      }
+      SX::sync(bar_id);
+      if (l < G::cyb) {
+        float t[G::cxb];
+#pragma unroll
+        for (int x = 0; x < G::cxb; ++x) t[x] = llf[c * 64 + l * G::cxb + x];
+        idct1d<G::cxb>(t);
+#pragma unroll
+        for (int x = 0; x < G::cxb; ++x) dcv[c][x] = t[x];
+      }
+      if (A.adjust) {
+        float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+        const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+        const int q = adjust_quant_sq<N, MODE>(u, wlane + (size_t)c * G::LANES * G::VALS, c, scale, mulc, orig, thr, l, owner, xch, bar_id);
+        maxq = max(maxq, q);
+        if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
+      }
+      if (it == 0) {
+#pragma unroll
+        for (int j = 0; j < G::VALS; ++j) uY[j] = u[j];
+      } else {
+        float* st = stash[it - 1];
+#pragma unroll
+        for (int j = 0; j < G::VALS; ++j) st[j * N + l] = u[j];   // lane-private column: no barrier needed
       }
     }
-    nz = group_isum<H>(nz);
+    int quant = orig;
+    if (A.adjust) {
+      // every lane computed the same maximum (the sums are group-wide); the group's lanes 0 hold the transform's value
+      quant = maxq;
+    } else { thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f; }
+    // ---- DC values and the integer quant field of the covered blocks
+    if (active && l < G::cyb) {
 #pragma unroll
-    for (int st = H / 2; st >= 1; st >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, st));
-    if (gl == 0) {
-      const int shared = (nz + n - 1) >> log2n;
-      A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nz;
-      A.lastk[(size_t)c * nblk + bi] = (uint16_t)last;
-      for (int j = 0; j < n; ++j) A.nzeros[(size_t)c * nblk + bi + (size_t)(j / cxb) * fd.bxs + (j % cxb)] = (uint8_t)shared;
+      for (int x = 0; x < G::cxb; ++x) {
+        const size_t bj = bi + (size_t)l * fd.bxs + x;
+        store_dc(A, bj, dcv[0][x], dcv[1][x], dcv[2][x]);
+        A.raw_qf[bj] = quant;
+      }
     }
+    // ---- pass B: quantise Y; its dequantised value feeds X and B; non-zero values are scattered in scan order
+    const float qac = scale * (float)quant;
+    const float inv_qac = inv_gs / (float)quant;
+    const int tx = bx >> 3, ty = by >> 3;
+    const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
+    const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
+    const uint16_t* invrow = A.inv + (size_t)l * G::VALS;
+    const float* dqY = A.dq + (size_t)1 * G::LANES * G::VALS + (size_t)l * G::VALS;
+    constexpr int log2n = G::ncov == 2 ? 1 : (G::ncov == 4 ? 2 : (G::ncov == 8 ? 3 : (G::ncov == 16 ? 4 : (G::ncov == 32 ? 5 : 6))));
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+      const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+      const int slot = it;
+      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+      if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
+      else if (G::xs * G::ys >= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { thr[i] -= 0.00744f * (float)(G::xs * G::ys); if (thr[i] < 0.5f) thr[i] = 0.5f; }
+      }
+      const float qac_mul = qac * (c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul));
+      const float factor = c == 0 ? x_factor : b_factor;
+      const float* wrow = wlane + (size_t)c * G::LANES * G::VALS;
+      const float* st = stash[it == 0 ? 0 : it - 1];
+      int nz = 0, last = 0;
+      if (owner) {
+#pragma unroll
+        for (int j4 = 0; j4 < G::VALS; j4 += 4) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j4));
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+          const uint2 i4 = __ldg(reinterpret_cast<const uint2*>(invrow + j4));
+          const uint32_t iv[4] = {i4.x & 0xFFFFu, i4.x >> 16, i4.y & 0xFFFFu, i4.y >> 16};
+          float4 d4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (c == 1) d4 = __ldg(reinterpret_cast<const float4*>(dqY + j4));
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 + e;
+            const int x = MODE == kModeWide2 ? l : j, y = MODE == kModeWide2 ? j : l;
+            float in;
+            if (c == 1) in = uY[j];
+            else in = __fmaf_rn(-factor, uY[j], st[j * N + l]);          // uY holds the dequantised Y by now
+            const float t = thr[(y >= G::HS / 2 ? 2 : 0) + (x >= G::W / 2 ? 1 : 0)];
+            const float val = (wv[e] * qac_mul) * in;
+            int q = (fabsf(val) >= t) ? (int)rintf(val) : 0;
+            if (x < G::xs && y < G::ys) q = 0;
+            q = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
+            if (c == 1) uY[j] = (quant_bias(1, q) * dv[e]) * inv_qac;
+            if (q != 0 && active) {
+              const int k = (int)iv[e];
+              const int jj = k >> 6;
+              const int cbx = bx + (jj % G::cxb), cby = by + (jj / G::cxb);
+              const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
+              const size_t blk = (size_t)g * kGroupBlocks + (size_t)(cby & 31) * 32 + (cbx & 31);
+              A.coeffs[(blk * 3 + slot) * 64 + (k & 63)] = (int16_t)q;
+              ++nz; last = max(last, k);
+            }
+          }
+        }
+      }
+      float cnt[1] = {(float)nz};                                       // <= 4096: exact in float
+      lane_sums<N, G::LANES, 1>(cnt, xch, l, bar_id);
+      float lastf[1] = {(float)last};
+      lane_maxs<N, G::LANES, 1>(lastf, xch, l, bar_id);
+      if (active && l == 0) {
+        const int nzt = (int)cnt[0];
+        const int shared = (nzt + G::ncov - 1) >> log2n;
+        A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nzt;
+        A.lastk[(size_t)c * nblk + bi] = (uint16_t)(int)lastf[0];
+        for (int jj = 0; jj < G::ncov; ++jj) A.nzeros[(size_t)c * nblk + bi + (size_t)(jj / G::cxb) * fd.bxs + (jj % G::cxb)] = (uint8_t)shared;
+      }
+    }
+    SX::sync(bar_id);   // buffers are reused by the next item
   }
-  __syncthreads();   // the buffers and cp_* are reused by the next transform
 }
 
-// all transforms of strategy S whose first block lies in the square: `mask` has one bit per block of the square
+// ------------------------------------------------------------------------------------------------ host side
 template <int S>
-__device__ void process_strategy(CoeffShared& sh, int warp, unsigned mask, int sbx, int sby, const CoeffArgs& A, int kind,
-                                 int order_class, int lane) {
-  constexpr int R = StratDim<S>::R, C = StratDim<S>::C;
-  constexpr int GS = R > C ? R : C, GPW = 32 / GS;
-  const int m = __popc(mask);
-  if constexpr (GS == 32 && kCoeffWarps == 4) {
-    // (mask is the same in every warp: the loop and the barriers inside are CTA-uniform)
-    for (int idx = 0; idx < m; ++idx) {
-      const int b = (int)__fns(mask, 0, idx + 1);
-      const int lx = b & 3, ly = b >> 2;
-      process_transform_cp<S>(sh, warp, lx * 8, ly * 8, sbx + lx, sby + ly, A, kind, order_class, lane);
-    }
-    return;
-  }
-  for (int base = warp * GPW; base < m; base += kCoeffWarps * GPW) {
-    const int idx = base + lane / GS;
-    const bool active = idx < m;
-    const int b = active ? (int)__fns(mask, 0, idx + 1) : 0;
-    const int lx = b & 3, ly = b >> 2;
-    process_transform<S>(sh, warp, active, lx * 8, ly * 8, sbx + lx, sby + ly, A, kind, order_class, lane);
-  }
+static void launch_coeff8(CoeffArgs A, int list_id, int kind, uint32_t* lists, const AcsTables& T, size_t nblk, cudaStream_t s) {
+  A.w = T.w[kind]; A.dq = T.dq[kind]; A.inv = nullptr;
+  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
+  ++g_kernel_launches;
+  k_coeff8<S><<<(unsigned)((nblk + 63) / 64), 64, 0, s>>>(A);
+}
+template <int N, int MODE>
+static void launch_coeffsq(CoeffArgs A, int list_id, const float* w, const float* dq, const uint16_t* inv, uint32_t* lists, size_t nblk,
+                           cudaStream_t s) {
+  using CG = CoeffSqGeom<N>;
+  A.w = w; A.dq = dq; A.inv = inv;
+  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
+  const size_t smem = CG::kSmemFloats * sizeof(float);
+  cudaFuncSetAttribute(k_coeffsq<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t max_items = nblk / (size_t)CoeffGeom<N, MODE>::ncov + 1;
+  size_t grid = (max_items + CG::kGroups - 1) / CG::kGroups;
+  if (grid > 148 * 8) grid = 148 * 8;
+  ++g_kernel_launches;
+  k_coeffsq<N, MODE><<<(unsigned)grid, CG::kThreads, smem, s>>>(A);
 }
 
-__global__ void __launch_bounds__(kCoeffWarps * 32) k_coeff_general(const float* __restrict__ X, const float* __restrict__ Y,
-                                                                    const float* __restrict__ B, const uint8_t* __restrict__ acs,
-                                                                    CoeffArgs A) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  CoeffShared& sh = *reinterpret_cast<CoeffShared*>(smem_raw);
-  const FrameDim& fd = A.fd;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int sbx = blockIdx.x * 4, sby = blockIdx.y * 4;
-  const int bw = min(4, fd.bxs - sbx), bh = min(4, fd.bys - sby);
-  for (int i = t; i < 32 * 32; i += kCoeffWarps * 32) {
-    const int y = i >> 5, x = i & 31;
-    const bool in = x < bw * 8 && y < bh * 8;
-    const size_t g = (size_t)(sby * 8 + y) * fd.pitch + (size_t)sbx * 8 + x;
-    sh.px[0][y * kTPitch + x] = in ? X[g] : 0.0f;
-    sh.px[1][y * kTPitch + x] = in ? Y[g] : 0.0f;
-    sh.px[2][y * kTPitch + x] = in ? B[g] : 0.0f;
-  }
-  // strategy of the square's blocks: lane b < 16 looks at block b; one ballot per strategy gives its transform list
-  int my_s = -1;
-  if (lane < 16) {
-    const int lx = lane & 3, ly = lane >> 2;
-    if (lx < bw && ly < bh) {
-      const uint8_t a = acs[(size_t)(sby + ly) * fd.bxs + sbx + lx];
-      if (a & 0x80) my_s = a & 0x7f;
-    }
-  }
-  __syncthreads();
-#define JXLB_STRATEGY(S, KIND, ORD) \
-  { const unsigned mk = __ballot_sync(0xffffffffu, my_s == S); if (mk) process_strategy<S>(sh, warp, mk, sbx, sby, A, KIND, ORD, lane); }
-  JXLB_STRATEGY(kStratDCT, 0, 0)
-  JXLB_STRATEGY(kStratDCT4X4, 3, 1)
-  JXLB_STRATEGY(kStratDCT4X8, 9, 1)
-  JXLB_STRATEGY(kStratDCT8X4, 9, 1)
-  JXLB_STRATEGY(kStratDCT16X8, 6, 4)
-  JXLB_STRATEGY(kStratDCT8X16, 6, 4)
-  JXLB_STRATEGY(kStratDCT16X16, 4, 2)
-  JXLB_STRATEGY(kStratDCT32X16, 8, 6)
-  JXLB_STRATEGY(kStratDCT16X32, 8, 6)
-  JXLB_STRATEGY(kStratDCT32X32, 5, 3)
-#undef JXLB_STRATEGY
+void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s) {
+  const size_t nblk = (size_t)fd.bxs * fd.bys;
+  cudaMemsetAsync(lists, 0, 64, s);
+  ++g_kernel_launches;
+  k_coeff_lists<<<(unsigned)((nblk + 255) / 256), 256, 0, s>>>(acs, (int)nblk, lists);
 }
 
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
                           const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s) {
-  // (function attributes are per device: set on every launch, a context may live on any GPU of the process)
-  cudaFuncSetAttribute(k_coeff_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoeffShared));
+                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s) {
+  const size_t nblk = (size_t)fd.bxs * fd.bys;
+  cudaMemsetAsync(coeffs, 0, (size_t)fd.num_groups * kGroupBlocks * 192 * sizeof(int16_t), s);
+  launch_coeff_lists(acs, fd, lists, s);
   CoeffArgs A;
-  A.fd = fd; A.qd = qd; A.T = T;
-  for (int i = 0; i < 13; ++i) A.inv_order[i] = inv_order[i];
-  A.cmap = cmap; A.x_qm_mul = x_qm_mul; A.b_qm_mul = b_qm_mul; A.adjust = adjust;
+  A.X = x; A.Y = y; A.B = b; A.fd = fd; A.qd = qd; A.cmap = cmap; A.x_qm_mul = x_qm_mul; A.b_qm_mul = b_qm_mul; A.adjust = adjust;
   A.raw_qf = raw_qf; A.coeffs = coeffs; A.dc_quant = dc_quant; A.nzeros = nzeros; A.nzcount = nzcount; A.lastk = lastk;
-  ++g_kernel_launches;
-  dim3 grid((fd.bxs + 3) / 4, (fd.bys + 3) / 4);
-  k_coeff_general<<<grid, kCoeffWarps * 32, sizeof(CoeffShared), s>>>(x, y, b, acs, A);
+  A.w = nullptr; A.dq = nullptr; A.inv = nullptr; A.list = nullptr; A.count = nullptr;
+  launch_coeff8<kStratDCT>(A, kListDCT, 0, lists, T, nblk, s);
+  launch_coeff8<kStratIDENTITY>(A, kListID, 1, lists, T, nblk, s);
+  launch_coeff8<kStratDCT2X2>(A, kList2X2, 2, lists, T, nblk, s);
+  launch_coeff8<kStratDCT4X4>(A, kList4X4, 3, lists, T, nblk, s);
+  launch_coeff8<kStratDCT4X8>(A, kList4X8, 9, lists, T, nblk, s);
+  launch_coeff8<kStratDCT8X4>(A, kList8X4, 9, lists, T, nblk, s);
+  // inv_order: [order class] natural, [13 + k] transposed for the wide strategy of order class 4 / 6 / 8
+  launch_coeffsq<16, kModeTall2>(A, kList16Tall, T.w[6], T.dq[6], inv_order[4], lists, nblk, s);
+  launch_coeffsq<16, kModeWide2>(A, kList16Wide, T.wT[6], T.dqT[6], inv_order[13], lists, nblk, s);
+  launch_coeffsq<16, kModeSq>(A, kList16Sq, T.w[4], T.dq[4], inv_order[2], lists, nblk, s);
+  launch_coeffsq<32, kModeTall2>(A, kList32Tall, T.w[8], T.dq[8], inv_order[6], lists, nblk, s);
+  launch_coeffsq<32, kModeWide2>(A, kList32Wide, T.wT[8], T.dqT[8], inv_order[14], lists, nblk, s);
+  launch_coeffsq<32, kModeSq>(A, kList32Sq, T.w[5], T.dq[5], inv_order[3], lists, nblk, s);
+  launch_coeffsq<64, kModeTall2>(A, kList64Tall, T.w[12], T.dq[12], inv_order[8], lists, nblk, s);
+  launch_coeffsq<64, kModeWide2>(A, kList64Wide, T.wT[12], T.dqT[12], inv_order[15], lists, nblk, s);
+  launch_coeffsq<64, kModeSq>(A, kList64Sq, T.w[11], T.dq[11], inv_order[7], lists, nblk, s);
 }
 
 }  // namespace jxlb

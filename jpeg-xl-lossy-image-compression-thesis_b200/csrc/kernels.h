@@ -18,12 +18,6 @@ void launch_raw_qf(const float* qf, const uint8_t* acs, const FrameDim& fd, cons
 // K4 (k_homog.cu)
 void launch_homogeneity(const float* x, const float* y, const float* b, const FrameDim& fd, float distance,
                         float* out, cudaStream_t s);
-// K7 (k_dct_quant.cu)
-void launch_dct8_quant(const float* x, const float* y, const float* b, const FrameDim& fd, const QuantDev* qd,
-                       const float* weights, const float* dequant_y, const uint8_t* izz, const int8_t* cmap,
-                       float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                       uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
-
 // K7, DCT8 frames, two threads per block with cp.async-staged tiles (k_dct8_v4.cu)
 int dct8_v4_bias_entries();
 void dct8_v4_host_tables(const uint8_t* izz64, float* bias, uint8_t* last_lut /* [2][4][256] */);
@@ -36,20 +30,28 @@ void launch_dct8_quant_v4(const float* x, const float* y, const float* b, const 
 struct AcsParams {
   float info_loss_multiplier, zeros_mul, cost_delta, distance, mul8x8, cmap_x, cmap_b;
   int factored_entropy, partitioning;   // H9 / H8 hooks of the thesis' proposals
+  int speed_tier;                       // 10 - effort (libjxl SpeedTier: hare = 5 ... tortoise = 1)
 };
-struct AcsTables { const float* w[17]; const float* dq[17]; };   // quantisation weights / their inverses per table kind
+// quantisation weights / their inverses per table kind; wT / dqT: the same tables transposed ([hf][vf] of the WIDE
+// strategy of kinds 6, 8, 12: the order a lane that owns one horizontal frequency reads them in)
+struct AcsTables { const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; };
+size_t acs_work_floats(const FrameDim& fd);   // candidate-value tables of the search
+size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-aligned squares (uint32 words)
 void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,
-                const FrameDim& fd, const AcsParams& P, const AcsTables& T, uint8_t* acs, float* est, cudaStream_t s);
+                const FrameDim& fd, const AcsParams& P, const AcsTables& T, float* work, uint32_t* jobs, uint8_t* acs, float* est,
+                cudaStream_t s);
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
                           const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, cudaStream_t s);
+                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s);
+void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s);   // bins the first blocks by strategy
+size_t coeff_list_words(const FrameDim& fd);  // per-class transform lists of k_coeff / k_recon (uint32 words)
 
 // K13 (k_recon.cu): per-channel sum of squared errors of the coded frame's reconstruction against the input pixels
 void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order,
                       const int8_t* cmap, float inv_qm_x, float inv_qm_b, const uint8_t* acs, const int32_t* raw_qf,
                       const int16_t* coeffs, const int16_t* dc_quant, const uint8_t* rgb, size_t stride, const float* tables,
-                      unsigned long long* sse3, cudaStream_t s);
+                      const uint32_t* lists, float* scratch_xyb, unsigned long long* sse3, cudaStream_t s);
 
 // ---- entropy stage -------------------------------------------------------------------------
 // one 2048x2048 DC group: rectangle in blocks, its 64x64-tile rectangle, first element / first block slot

@@ -73,7 +73,7 @@ enum Strategy : uint8_t {
   DCT = 0, IDENTITY = 1, DCT2X2 = 2, DCT4X4 = 3, DCT16X16 = 4, DCT32X32 = 5,
   DCT16X8 = 6, DCT8X16 = 7, DCT32X8 = 8, DCT8X32 = 9, DCT32X16 = 10, DCT16X32 = 11,
   DCT4X8 = 12, DCT8X4 = 13, AFV0 = 14, AFV1 = 15, AFV2 = 16, AFV3 = 17,
-  DCT64X64 = 18, kNumStrategies = 27
+  DCT64X64 = 18, DCT64X32 = 19, DCT32X64 = 20, kNumStrategies = 27
 };
 extern const uint8_t kCoveredX[27];   // covered blocks, horizontal
 extern const uint8_t kCoveredY[27];   // covered blocks, vertical
@@ -89,7 +89,7 @@ float CbrtPos(float x);
 void RgbToXyb(const uint8_t* rgb, int w, int h, size_t stride, const FrameDim& fd, float* x, float* y, float* b);
 
 // ---------------------------------------------------------------- stage: transforms (U5)
-// 1-D scaled DCT-II / its inverse over `n` floats with stride; n in {2,4,8,16,32}
+// 1-D scaled DCT-II / its inverse over `n` floats with stride; n in {2,4,8,16,32,64}
 void Dct1D(const float* in, int in_stride, float* out, int out_stride, int n);
 void Idct1D(const float* in, int in_stride, float* out, int out_stride, int n);
 // 2-D transform of a rows x cols pixel rectangle; output has the long side
@@ -108,6 +108,7 @@ void LowestFrequenciesFromDc(int strategy, const float* dc, int dc_stride, float
 int QuantWeights(int kind, std::vector<float>* w);
 float FastLog2f(float x);
 float FastPow2f(float x);
+float FastPowf(float base, float e);   // FastPow2f(FastLog2f(base) * e)
 
 // ---------------------------------------------------------------- stage: homogeneity (H1-H9)
 struct HomogConfig {

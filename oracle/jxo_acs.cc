@@ -1,27 +1,41 @@
 // ORACLE (test infrastructure) — stage U4: AC-strategy (block partition) search with the thesis'
-// two hooks.
+// two hooks.  Restates libjxl lib/jxl/enc_ac_strategy.cc (the file the proposals patch) as it looks
+// in the diffs' pre-image (blob 4aafd7a5, proposals/*.diff:2): the function bodies are recalled
+// [UPSTREAM], the call structure is pinned by the diff context lines cited below.
 //
-//  * H8 (proposals/homogeneity-partitioning.diff:213-235, hook :272-276; combined.diff:270-274):
-//    after the 8x8 search, a block whose winner is plain DCT8 is overridden by
-//    HomogeneityPartition(); its entropy estimate is NOT recomputed.
-//  * H9 (proposals/homogeneity-factored-entropy.diff:248-253; combined.diff:248-253): every
-//    EstimateEntropy() result is multiplied by 0.8 * (r_h + r_v + r_d) / 3 of the candidate's
-//    top-left 8x8 block (double multiply, narrowed on return).  NaN candidates lose the 8x8
-//    argmin (`entropy < best` is false) but WIN merges (`candidate >= current` is false), exactly
-//    as in the patched libjxl (diff :266, :296).
-//  * H10: the control-flow shape of ProcessRectACS in the diff context (:259-401): 8x8 search ->
-//    aligned 16x16 squares (square vs the two half splits) -> aligned 32x32 squares.
+//  * H8  proposals/homogeneity-partitioning.diff:213-235, hook :272-276 (combined.diff:270-274): after the
+//        8x8 search a block whose winner is plain DCT8 is overridden by HomogeneityPartition(); its
+//        entropy estimate is NOT recomputed.
+//  * H9  proposals/homogeneity-factored-entropy.diff:248-253 (combined.diff:248-253): every EstimateEntropy()
+//        result is multiplied by 0.8 * (r_h + r_v + r_d) / 3 of the candidate's top-left 8x8 block (double
+//        multiply, narrowed on return).  A NaN candidate loses the 8x8 argmin (`entropy < best`, :266) and
+//        every `<` / std::min test of FindBestFirstLevelDivisionForSquare, but is ACCEPTED by TryMergeAcs
+//        (`if (entropy_candidate >= entropy_current) return;`, combined.diff context "@@ -602,7 +835,7").
+//  * H10 control flow of ProcessRectACS (combined.diff context @@ -911 .. -1010): per 64x64 tile, 8x8 search ->
+//        merge table {16X8, 8X16, 16X32, 32X16, 64X32, 32X64} where the aligned 2-, 4- and 8-block squares go
+//        through FindBestFirstLevelDivisionForSquare(2 | 4 | 8, ...) and everything the squares do not cover
+//        (last column / row of ragged tiles, the two 64X32 halves, the lower 32X64) through
+//        TryMergeAcs(type, ..., priority) -> non-aligned 16-level squares ((cy | cx) % 2 != 0) -> non-aligned
+//        32-level squares (step 2 below glacier).  Efforts: < 5 no search; 5 (hare) no DCT4X8 / DCT8X4
+//        candidates and no non-aligned passes; 6..9 the full search.
 //
-// Everything else (the cost model EstimateEntropy, the candidate multipliers) restates libjxl
-// enc_ac_strategy.cc from recall [UPSTREAM, SURVEY.md Appendix U.4-7] over the transform set this
-// repo emits (DCT8, 4x4, 4x8, 8x4, 16x8, 8x16, 16x16, 32x16, 16x32, 32x32); the 64-sized
-// transforms, IDENTITY / DCT2X2 / AFV and the non-aligned re-tries are out of scope.
-// parity unpinned.
+// Defined behaviour where the recalled control flow would leave an invalid map: TryMergeAcs only looks at
+// `priority`, which FindBestFirstLevelDivisionForSquare never sets, so the lower 32X64 candidate could be
+// accepted on top of a 64X32 / 64X64 the square pass chose (always when it is NaN under H9).  This
+// restatement rejects a TryMergeAcs candidate whose rectangle is straddled by an existing transform.
 //
-// Numerics contract: block-wide float sums are per-row sequential sums followed by an xor-butterfly
-// over the rows (the association a warp-shuffle reduction produces); see DESIGN.md "Numerics".
+// Candidate set: DCT, DCT4X4, DCT2X2, DCT4X8, DCT8X4, IDENTITY at the 8x8 level (AFV0-3 are left out: their
+// 16x16 basis is a table of constants that cannot be derived offline), every DCT size of the merge table.
+// parity unpinned (see jxo.h).
+//
+// Numerics contract (DESIGN.md "Numerics"): a sum over a transform is defined as per-lane sequential sums
+// followed by an xor-butterfly over the lanes.  Entropy term: lane = horizontal frequency hf, sequential
+// over vf (8x8 special layouts: lane = storage row, sequential over the row).  Loss term: lane = pixel row,
+// sequential over x.
 #include "jxo_frame.h"
 #include "jxo_stages.h"
+
+#include <cfloat>
 
 namespace jxo {
 
@@ -30,13 +44,14 @@ namespace {
 struct AcsConfig {
   float info_loss_multiplier, zeros_mul, cost_delta;
   float distance;
+  int speed_tier;          // 10 - effort (libjxl SpeedTier: hare = 5, squirrel = 3, tortoise = 1)
   bool factored_entropy;   // H9 active
   bool partitioning;       // H8 active
 };
 
-float ButterflySum(const float* rows, int n) {
-  float p[32], q[32];
-  for (int i = 0; i < n; ++i) p[i] = rows[i];
+float ButterflySum(const float* lanes, int n) {
+  float p[64], q[64];
+  for (int i = 0; i < n; ++i) p[i] = lanes[i];
   for (int st = n / 2; st >= 1; st /= 2) {
     for (int i = 0; i < n; ++i) q[i] = p[i] + p[i ^ st];
     for (int i = 0; i < n; ++i) p[i] = q[i];
@@ -44,68 +59,94 @@ float ButterflySum(const float* rows, int n) {
   return p[0];
 }
 
-// libjxl enc_ac_strategy.cc EstimateEntropy (restated) + H9
+inline bool IsPlainDct(int s) {
+  return s == DCT || s == DCT16X16 || s == DCT32X32 || (s >= DCT16X8 && s <= DCT16X32) || (s >= DCT64X64 && s <= DCT32X64);
+}
+
+// libjxl enc_ac_strategy.cc EstimateEntropy (restated; last lines pinned by combined.diff:245-253) + H9
 float EstimateEntropy(const Frame& f, const AcsConfig& cfg, int s, float entropy_mul, int bx, int by) {
   const FrameDim& fd = f.fd;
   const EncTables& T = GetTables();
   const int cx = kCoveredX[s], cy = kCoveredY[s], n = cx * cy;
   const int rows = cy * 8, cols = cx * 8, size = rows * cols;
-  const int W = std::max(rows, cols), H = std::min(rows, cols);   // coefficient block: H rows of W
-  const int xs = W / 8, ys = H / 8;
-  float q = f.qf_float[(size_t)by * fd.bxs + bx];
-  for (int iy = 0; iy < cy; ++iy) for (int ix = 0; ix < cx; ++ix) q = std::max(q, f.qf_float[(size_t)(by + iy) * fd.bxs + bx + ix]);
-  const float inv_q = 1.0f / q;
+  // quant_norm16: the block's quant, the larger of two, or the 16-norm mean over more
+  float quant_norm16 = 0.0f;
+  if (n == 1) {
+    quant_norm16 = f.qf_float[(size_t)by * fd.bxs + bx];
+  } else if (n == 2) {
+    const float a = f.qf_float[(size_t)by * fd.bxs + bx];
+    const float b = cy == 2 ? f.qf_float[(size_t)(by + 1) * fd.bxs + bx] : f.qf_float[(size_t)by * fd.bxs + bx + 1];
+    quant_norm16 = std::max(a, b);
+  } else {
+    for (int iy = 0; iy < cy; ++iy) for (int ix = 0; ix < cx; ++ix) {
+      float qval = f.qf_float[(size_t)(by + iy) * fd.bxs + bx + ix];
+      qval *= qval; qval *= qval; qval *= qval;
+      quant_norm16 += qval * qval;
+    }
+    quant_norm16 /= (float)n;
+    quant_norm16 = FastPowf(quant_norm16, 1.0f / 16.0f);
+  }
   const int kind = kQuantKind[s];
   const float* weights = T.weights[kind].data();
   const float* dequant = T.dequant[kind].data();
-  std::vector<float> coef((size_t)3 * size), err(size), pix((size_t)rows * cols);
+  std::vector<float> coef((size_t)3 * size), mem(size), pix((size_t)rows * cols);
   for (int c = 0; c < 3; ++c)
     TransformFromPixels(s, &f.xyb[c][(size_t)by * 8 * fd.pitch + (size_t)bx * 8], fd.pitch, &coef[(size_t)c * size]);
   const int tx = bx / 8, ty = by / 8;
   const float cmapf[3] = {0.0f + (float)f.cmap[(size_t)ty * fd.txs + tx] / 84.0f, 0.0f,
                           1.0f + (float)f.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f};
-  static const float kChannelMul[3] = {10.2f, 1.0f, 1.03f};
-  float entropy = 0.0f, loss = 0.0f;
+  // pow(kChannelMul[c], 8.0) of {10.2, 1.0, 1.03}, narrowed to float
+  static const float kChannelMul8[3] = {1.1716594e+08f, 1.0f, 1.2667701e+00f};
+  // lane / sequence position of storage index k (see the numerics note above)
+  const bool plain = IsPlainDct(s);
+  const int lanes = plain ? cols : 8;
+  const int per_lane = size / lanes;
+  auto storage_index = [&](int lane, int j) {
+    if (!plain) return lane * 8 + j;
+    return rows >= cols ? lane * rows + j : j * cols + lane;   // (hf = lane, vf = j)
+  };
+  float entropy = 0.0f, loss_sum = 0.0f;
   for (int c = 0; c < 3; ++c) {
-    float ent_row[32];
+    float ent_lane[64];
     int nz = 0;
-    for (int y = 0; y < H; ++y) {
+    for (int l = 0; l < lanes; ++l) {
       float acc = 0.0f;
-      for (int x = 0; x < W; ++x) {
-        const int k = y * W + x;
-        if (x < xs && y < ys) { err[k] = 0.0f; continue; }
-        const float v_in = c == 1 ? coef[(size_t)size + k] : fmaf(-cmapf[c], coef[(size_t)size + k], coef[(size_t)c * size + k]);
-        const float val = v_in * (weights[(size_t)c * size + k] * q);
+      for (int j = 0; j < per_lane; ++j) {
+        const int k = storage_index(l, j);
+        const float in = coef[(size_t)c * size + k];
+        const float v_in = cmapf[c] == 0.0f ? in : fmaf(-cmapf[c], coef[(size_t)size + k], in);
+        const float val = v_in * (weights[(size_t)c * size + k] * quant_norm16);
         const float rval = rintf(val);
         const float diff = val - rval;
+        mem[k] = dequant[(size_t)c * size + k] * diff;
         acc += sqrtf(fabsf(rval));
         nz += rval != 0.0f;
-        err[k] = diff * (dequant[(size_t)c * size + k] * inv_q);
       }
-      ent_row[y] = acc;
+      ent_lane[l] = acc;
     }
-    float ent = ButterflySum(ent_row, H) * cfg.cost_delta;
+    float ent = ButterflySum(ent_lane, lanes) * cfg.cost_delta;
     const int nbits = CeilLog2((uint32_t)nz + 1) + 1;
     ent += cfg.zeros_mul * (float)(CeilLog2((uint32_t)nbits + 17) + nbits);
     entropy += ent;
     // information loss: masked 8-norm of the quantisation error in the pixel domain
-    TransformToPixels(s, err.data(), pix.data(), cols);
-    float loss_row[32];
+    TransformToPixels(s, mem.data(), pix.data(), cols);
+    float loss_row[64];
     for (int r = 0; r < rows; ++r) {
       float acc = 0.0f;
       const float* m = &f.mask1x1[(size_t)(by * 8 + r) * fd.pitch + (size_t)bx * 8];
       for (int x = 0; x < cols; ++x) {
-        const float t = pix[(size_t)r * cols + x] * m[x];
+        const float t = fabsf(m[x]) * pix[(size_t)r * cols + x];
         const float t2 = t * t, t4 = t2 * t2;
         acc += t4 * t4;
       }
       loss_row[r] = acc;
     }
-    const float mean8 = ButterflySum(loss_row, rows) / (float)(rows * cols);
-    loss += kChannelMul[c] * sqrtf(sqrtf(sqrtf(mean8)));
+    loss_sum += kChannelMul8[c] * ButterflySum(loss_row, rows);
   }
-  const float loss_scalar = loss * (float)(n * 64) * inv_q;
-  float ret = entropy * entropy_mul + cfg.info_loss_multiplier * loss_scalar;
+  const float npx = (float)(n * 64);
+  const float loss_scalar = sqrtf(sqrtf(sqrtf(loss_sum / npx))) * npx / quant_norm16;
+  float ret = entropy * entropy_mul;
+  ret += cfg.info_loss_multiplier * loss_scalar;
   if (cfg.factored_entropy) {
     const float* r = &f.homog[((size_t)by * fd.bxs + bx) * 3];
     const float avg_r = (r[0] + r[1] + r[2]) / 3;
@@ -114,61 +155,250 @@ float EstimateEntropy(const Frame& f, const AcsConfig& cfg, int s, float entropy
   return ret;
 }
 
-void SetStrategy(Frame* f, int s, int bx, int by, float est) {
-  const FrameDim& fd = f->fd;
-  const int cx = kCoveredX[s], cy = kCoveredY[s];
-  for (int iy = 0; iy < cy; ++iy) for (int ix = 0; ix < cx; ++ix) {
-    const size_t i = (size_t)(by + iy) * fd.bxs + bx + ix;
-    f->acs[i] = (uint8_t)(s | ((ix == 0 && iy == 0) ? 0x80 : 0));
-    f->acs_entropy[i] = (ix == 0 && iy == 0) ? est : 0.0f;
+// ---- AcStrategyImage view of Frame::acs ------------------------------------------------------------
+struct AcsImage {
+  Frame* f;
+  int xsize() const { return f->fd.bxs; }
+  int ysize() const { return f->fd.bys; }
+  bool IsFirst(int x, int y) const { return f->acs[(size_t)y * f->fd.bxs + x] & 0x80; }
+  int Raw(int x, int y) const { return f->acs[(size_t)y * f->fd.bxs + x] & 0x7f; }
+  void Set(int x, int y, int s) {
+    for (int iy = 0; iy < kCoveredY[s]; ++iy) for (int ix = 0; ix < kCoveredX[s]; ++ix)
+      f->acs[(size_t)(y + iy) * f->fd.bxs + x + ix] = (uint8_t)(s | ((ix == 0 && iy == 0) ? 0x80 : 0));
+  }
+};
+
+// libjxl MultiBlockTransformCrossesHorizontalBoundary: does a transform that started above row y reach into it
+// somewhere in [start_x, end_x)?
+bool CrossesHorizontalBoundary(const AcsImage& a, int start_x, int y, int end_x) {
+  if (start_x >= a.xsize() || y >= a.ysize()) return false;
+  if (y % 8 == 0) return false;   // nothing crosses 64x64 boundaries
+  end_x = std::min(end_x, a.xsize());
+  const int start_x_limit = start_x & ~7;
+  while (start_x != start_x_limit && !a.IsFirst(start_x, y)) --start_x;
+  for (int x = start_x; x < end_x;) {
+    if (a.IsFirst(x, y)) x += kCoveredX[a.Raw(x, y)];
+    else return true;
+  }
+  return false;
+}
+
+bool CrossesVerticalBoundary(const AcsImage& a, int x, int start_y, int end_y) {
+  if (x >= a.xsize() || start_y >= a.ysize()) return false;
+  if (x % 8 == 0) return false;
+  end_y = std::min(end_y, a.ysize());
+  const int start_y_limit = start_y & ~7;
+  while (start_y != start_y_limit && !a.IsFirst(x, start_y)) --start_y;
+  for (int y = start_y; y < end_y;) {
+    if (a.IsFirst(x, y)) y += kCoveredY[a.Raw(x, y)];
+    else return true;
+  }
+  return false;
+}
+
+void SetEntropyForTransform(int cx, int cy, int s, float entropy, float* entropy_estimate) {
+  for (int dy = 0; dy < kCoveredY[s]; ++dy) for (int dx = 0; dx < kCoveredX[s]; ++dx) entropy_estimate[(cy + dy) * 8 + cx + dx] = 0.0f;
+  entropy_estimate[cy * 8 + cx] = entropy;
+}
+
+inline float StdMin(float a, float b) { return (b < a) ? b : a; }   // std::min(a, b): NaN in `a` stays
+
+// libjxl FindBest8x8Transform (candidate table recalled, hook H8 pinned by combined.diff:270-274)
+int FindBest8x8Transform(const Frame& f, const AcsConfig& cfg, int bx, int by, float* entropy_out) {
+  struct Try { int type; int tier_max; double mul; };
+  static const Try kTransforms8x8[] = {
+      {DCT, 9, 0.8}, {DCT4X4, 5, 1.08}, {DCT2X2, 5, 0.95}, {DCT4X8, 4, 0.85931637428340035},
+      {DCT8X4, 4, 0.85931637428340035}, {IDENTITY, 5, 1.0427542510634957},
+      // {AFV0..3, 4, 0.81779489591359944}: not built (basis constants not derivable offline)
+  };
+  double best = 1e30;
+  int best_tx = DCT;
+  const float d = cfg.distance;
+  for (const Try& tx : kTransforms8x8) {
+    if (tx.tier_max < cfg.speed_tier) continue;
+    float entropy_mul = (float)(tx.mul / kTransforms8x8[0].mul);
+    if ((tx.type == DCT2X2 || tx.type == IDENTITY) && d < 5.0f) {
+      const float kFavor2X2AtHighQuality = 0.4f;
+      const float w = (5.0f - d) / 5.0f;
+      entropy_mul -= kFavor2X2AtHighQuality * (w * w);
+    }
+    if (tx.type != DCT && tx.type != DCT2X2 && tx.type != IDENTITY && d > 4.0f) {
+      const float kAvoidEntropyOfTransforms = 0.5f;
+      float mul = 1.0f;
+      if (d < 12.0f) mul *= (12.0f - 4.0f) / (d - 4.0f);
+      entropy_mul += kAvoidEntropyOfTransforms * mul;      // (combined.diff context "@@ -566,7 +793,7")
+    }
+    const float entropy = EstimateEntropy(f, cfg, tx.type, entropy_mul, bx, by);
+    if ((double)entropy < best) { best_tx = tx.type; best = (double)entropy; }
+  }
+  *entropy_out = (float)best;
+  if (cfg.partitioning && best_tx == DCT) {
+    const float* r = &f.homog[((size_t)by * f.fd.bxs + bx) * 3];
+    best_tx = HomogeneityPartition(r[0], r[1], r[2], d);
+  }
+  return best_tx;
+}
+
+// libjxl TryMergeAcs (combined.diff context "@@ -586,7 +819,7" .. "@@ -602,7 +835,7")
+void TryMergeAcs(Frame* f, const AcsConfig& cfg, int s, int bx, int by, int cx, int cy, float entropy_mul,
+                 uint8_t candidate_priority, uint8_t* priority, float* entropy_estimate) {
+  AcsImage a{f};
+  const int cvx = kCoveredX[s], cvy = kCoveredY[s];
+  float entropy_current = 0.0f;
+  for (int iy = 0; iy < cvy; ++iy) for (int ix = 0; ix < cvx; ++ix) {
+    if (priority[(cy + iy) * 8 + cx + ix] >= candidate_priority) return;   // would reuse allocated blocks
+    entropy_current += entropy_estimate[(cy + iy) * 8 + cx + ix];
+  }
+  // defined behaviour (see the header): an existing transform must not straddle the candidate's rectangle
+  if (CrossesHorizontalBoundary(a, bx + cx, by + cy, bx + cx + cvx) || CrossesHorizontalBoundary(a, bx + cx, by + cy + cvy, bx + cx + cvx) ||
+      CrossesVerticalBoundary(a, bx + cx, by + cy, by + cy + cvy) || CrossesVerticalBoundary(a, bx + cx + cvx, by + cy, by + cy + cvy)) return;
+  const float entropy_candidate = EstimateEntropy(*f, cfg, s, entropy_mul, bx + cx, by + cy);
+  if (entropy_candidate >= entropy_current) return;
+  for (int iy = 0; iy < cvy; ++iy) for (int ix = 0; ix < cvx; ++ix) {
+    entropy_estimate[(cy + iy) * 8 + cx + ix] = 0.0f;
+    priority[(cy + iy) * 8 + cx + ix] = candidate_priority;
+  }
+  a.Set(bx + cx, by + cy, s);
+  entropy_estimate[cy * 8 + cx] = entropy_candidate;
+}
+
+// libjxl FindBestFirstLevelDivisionForSquare (combined.diff context "@@ -669,7 +902,7" .. "@@ -748,7 +981,7")
+void FindBestFirstLevelDivisionForSquare(Frame* f, const AcsConfig& cfg, int blocks, bool allow_square_transform, int bx, int by,
+                                         int cx, int cy, float entropy_mul_JXK, float entropy_mul_JXJ, float* entropy_estimate) {
+  AcsImage a{f};
+  const int blocks_half = blocks / 2;
+  const int acs_rawJXK = blocks == 2 ? DCT16X8 : (blocks == 4 ? DCT32X16 : DCT64X32);   // J rows x K columns
+  const int acs_rawKXJ = blocks == 2 ? DCT8X16 : (blocks == 4 ? DCT16X32 : DCT32X64);
+  const int acs_rawJXJ = blocks == 2 ? DCT16X16 : (blocks == 4 ? DCT32X32 : DCT64X64);
+  // can a JXJ block be considered here at all? (needed for the 'floating' positions)
+  if (CrossesHorizontalBoundary(a, bx + cx, by + cy, bx + cx + blocks) ||
+      CrossesHorizontalBoundary(a, bx + cx, by + cy + blocks, bx + cx + blocks) ||
+      CrossesVerticalBoundary(a, bx + cx, by + cy, by + cy + blocks) ||
+      CrossesVerticalBoundary(a, bx + cx + blocks, by + cy, by + cy + blocks)) return;
+  const bool allow_JXK = !CrossesVerticalBoundary(a, bx + cx + blocks_half, by + cy, by + cy + blocks);
+  const bool allow_KXJ = !CrossesHorizontalBoundary(a, bx + cx, by + cy + blocks_half, bx + cx + blocks);
+  float entropy[2][2] = {};
+  for (int dy = 0; dy < blocks; ++dy) for (int dx = 0; dx < blocks; ++dx)
+    entropy[dy / blocks_half][dx / blocks_half] += entropy_estimate[(cy + dy) * 8 + cx + dx];
+  float entropy_JXK_left = FLT_MAX, entropy_JXK_right = FLT_MAX, entropy_KXJ_top = FLT_MAX, entropy_KXJ_bottom = FLT_MAX,
+        entropy_JXJ = FLT_MAX;
+  if (allow_JXK) {
+    if (a.Raw(bx + cx, by + cy) != acs_rawJXK)
+      entropy_JXK_left = EstimateEntropy(*f, cfg, acs_rawJXK, entropy_mul_JXK, bx + cx, by + cy);
+    if (a.Raw(bx + cx + blocks_half, by + cy) != acs_rawJXK)
+      entropy_JXK_right = EstimateEntropy(*f, cfg, acs_rawJXK, entropy_mul_JXK, bx + cx + blocks_half, by + cy);
+  }
+  if (allow_KXJ) {
+    if (a.Raw(bx + cx, by + cy) != acs_rawKXJ)
+      entropy_KXJ_top = EstimateEntropy(*f, cfg, acs_rawKXJ, entropy_mul_JXK, bx + cx, by + cy);
+    if (a.Raw(bx + cx, by + cy + blocks_half) != acs_rawKXJ)
+      entropy_KXJ_bottom = EstimateEntropy(*f, cfg, acs_rawKXJ, entropy_mul_JXK, bx + cx, by + cy + blocks_half);
+  }
+  if (allow_square_transform)
+    entropy_JXJ = EstimateEntropy(*f, cfg, acs_rawJXJ, entropy_mul_JXJ, bx + cx, by + cy);
+  // the square can have JXK or KXJ transforms, not both
+  const float costJxN = StdMin(entropy_JXK_left, entropy[0][0] + entropy[1][0]) + StdMin(entropy_JXK_right, entropy[0][1] + entropy[1][1]);
+  const float costNxJ = StdMin(entropy_KXJ_top, entropy[0][0] + entropy[0][1]) + StdMin(entropy_KXJ_bottom, entropy[1][0] + entropy[1][1]);
+  if (entropy_JXJ < costJxN && entropy_JXJ < costNxJ) {
+    a.Set(bx + cx, by + cy, acs_rawJXJ);
+    SetEntropyForTransform(cx, cy, acs_rawJXJ, entropy_JXJ, entropy_estimate);
+  } else if (costJxN < costNxJ) {
+    if (entropy_JXK_left < entropy[0][0] + entropy[1][0]) {
+      a.Set(bx + cx, by + cy, acs_rawJXK);
+      SetEntropyForTransform(cx, cy, acs_rawJXK, entropy_JXK_left, entropy_estimate);
+    }
+    if (entropy_JXK_right < entropy[0][1] + entropy[1][1]) {
+      a.Set(bx + cx + blocks_half, by + cy, acs_rawJXK);
+      SetEntropyForTransform(cx + blocks_half, cy, acs_rawJXK, entropy_JXK_right, entropy_estimate);
+    }
+  } else {
+    if (entropy_KXJ_top < entropy[0][0] + entropy[0][1]) {
+      a.Set(bx + cx, by + cy, acs_rawKXJ);
+      SetEntropyForTransform(cx, cy, acs_rawKXJ, entropy_KXJ_top, entropy_estimate);
+    }
+    if (entropy_KXJ_bottom < entropy[1][0] + entropy[1][1]) {
+      a.Set(bx + cx, by + cy + blocks_half, acs_rawKXJ);
+      SetEntropyForTransform(cx, cy + blocks_half, acs_rawKXJ, entropy_KXJ_bottom, entropy_estimate);
+    }
   }
 }
 
-// One aligned square of `blocks` x `blocks` (2 or 4): the square transform against the two ways of
-// halving it against what is there now (libjxl FindBestFirstLevelDivisionForSquare, simplified to
-// aligned candidates).  "Horizontal" halves are wide transforms (top / bottom), "vertical" halves
-// are tall ones (left / right).
-void MergeSquare(Frame* f, const AcsConfig& cfg, int blocks, int sx, int sy) {
+// libjxl ProcessRectACS for one 64x64 tile: (bx, by) first block, rxs x rys blocks (combined.diff context @@ -911 .. -1010)
+void ProcessRectACS(Frame* f, const AcsConfig& cfg, int bx, int by, int rxs, int rys) {
+  AcsImage a{f};
   const FrameDim& fd = f->fd;
-  const int half = blocks / 2;
-  const int s_wide = blocks == 2 ? DCT8X16 : DCT16X32;    // half rows x full cols
-  const int s_tall = blocks == 2 ? DCT16X8 : DCT32X16;    // full rows x half cols
-  const int s_sq = blocks == 2 ? DCT16X16 : DCT32X32;
-  const float mul_half = blocks == 2 ? 1.25f : 1.5f;
-  const float mul_sq = blocks == 2 ? 1.35f : 1.5f;
-  auto region = [&](int x0, int y0, int w, int h) {
-    float acc = 0.0f;
-    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) acc += f->acs_entropy[(size_t)(sy + y0 + y) * fd.bxs + sx + x0 + x];
-    return acc;
+  float entropy_estimate[64] = {};
+  const float mul8x8 = 1.0f + -0.4f / (cfg.distance + 1.4f);
+  for (int iy = 0; iy < rys; ++iy) for (int ix = 0; ix < rxs; ++ix) {
+    float entropy = 0.0f;
+    const int best_of_8x8s = FindBest8x8Transform(*f, cfg, bx + ix, by + iy, &entropy);
+    a.Set(bx + ix, by + iy, best_of_8x8s);
+    entropy_estimate[iy * 8 + ix] = entropy * mul8x8;
+  }
+  struct MergeTry { int type; uint8_t priority; uint8_t decoding_speed_tier_max_limit; float entropy_mul; };
+  const float entropy_mul16X8 = 1.25f, entropy_mul16X16 = 1.35f, entropy_mul16X32 = 1.5f, entropy_mul32X32 = 1.5f,
+              entropy_mul64X32 = 2.26f, entropy_mul64X64 = 2.26f;
+  const MergeTry kTransformsForMerge[6] = {
+      {DCT16X8, 2, 4, entropy_mul16X8},   {DCT8X16, 2, 4, entropy_mul16X8},   {DCT16X32, 4, 4, entropy_mul16X32},
+      {DCT32X16, 4, 4, entropy_mul16X32}, {DCT64X32, 6, 1, entropy_mul64X32}, {DCT32X64, 6, 1, entropy_mul64X32},
   };
-  float cur_h[2], cur_v[2], e_h[2], e_v[2];
-  for (int i = 0; i < 2; ++i) {
-    cur_h[i] = region(0, i * half, blocks, half);
-    cur_v[i] = region(i * half, 0, half, blocks);
-    e_h[i] = EstimateEntropy(*f, cfg, s_wide, mul_half, sx, sy + i * half);
-    e_v[i] = EstimateEntropy(*f, cfg, s_tall, mul_half, sx + i * half, sy);
+  uint8_t priority[64] = {};
+  const int decoding_speed_tier = 0;
+  const bool enable_32x32 = decoding_speed_tier < 4;
+  for (const MergeTry& tx : kTransformsForMerge) {
+    if (tx.decoding_speed_tier_max_limit < decoding_speed_tier) continue;
+    const int cvx = kCoveredX[tx.type], cvy = kCoveredY[tx.type];
+    for (int cy = 0; cy + cvy - 1 < rys; cy += cvy) {
+      for (int cx = 0; cx + cvx - 1 < rxs; cx += cvx) {
+        if (cy + 7 < rys && cx + 7 < rxs) {
+          if (decoding_speed_tier < 4 && tx.type == DCT32X64) {
+            if ((cy | cx) % 8 == 0)
+              FindBestFirstLevelDivisionForSquare(f, cfg, 8, true, bx, by, cx, cy, tx.entropy_mul, entropy_mul64X64, entropy_estimate);
+            continue;
+          } else if (tx.type == DCT32X16) {
+            continue;
+          }
+        }
+        if ((tx.type == DCT16X32 && cy % 4 != 0) || (tx.type == DCT32X16 && cx % 4 != 0)) continue;   // covered by the 32x32 squares
+        if (cy + 3 < rys && cx + 3 < rxs) {
+          if (tx.type == DCT16X32) {
+            if ((cy | cx) % 4 == 0)
+              FindBestFirstLevelDivisionForSquare(f, cfg, 4, enable_32x32, bx, by, cx, cy, tx.entropy_mul, entropy_mul32X32, entropy_estimate);
+            continue;
+          } else if (tx.type == DCT32X16) {
+            continue;
+          }
+        }
+        if ((tx.type == DCT16X32 && cy % 4 != 0) || (tx.type == DCT32X16 && cx % 4 != 0)) continue;
+        if (cy + 1 < rys && cx + 1 < rxs) {
+          if (tx.type == DCT8X16) {
+            if ((cy | cx) % 2 == 0)
+              FindBestFirstLevelDivisionForSquare(f, cfg, 2, true, bx, by, cx, cy, tx.entropy_mul, entropy_mul16X16, entropy_estimate);
+            continue;
+          } else if (tx.type == DCT16X8) {
+            continue;
+          }
+        }
+        // no square covers this position: the normal integral transform merging process
+        TryMergeAcs(f, cfg, tx.type, bx, by, cx, cy, tx.entropy_mul, tx.priority, priority, entropy_estimate);
+      }
+    }
   }
-  const float e_s = EstimateEntropy(*f, cfg, s_sq, mul_sq, sx, sy);
-  bool take_h[2], take_v[2];
-  float cost_h = 0.0f, cost_v = 0.0f;
-  for (int i = 0; i < 2; ++i) {
-    take_h[i] = !(e_h[i] >= cur_h[i]);   // NaN candidates are accepted (H9 semantics, diff :296)
-    take_v[i] = !(e_v[i] >= cur_v[i]);
-    cost_h += take_h[i] ? e_h[i] : cur_h[i];
-    cost_v += take_v[i] ? e_v[i] : cur_v[i];
+  if (cfg.speed_tier < 5) {   // `if (cparams.speed_tier >= SpeedTier::kHare) return;`
+    // non-aligned matching: a few more 16X8, 8X16 and 16X16 between the non-2-aligned blocks
+    for (int cy = 0; cy + 1 < rys; ++cy) for (int cx = 0; cx + 1 < rxs; ++cx) {
+      if ((cy | cx) % 2 != 0)
+        FindBestFirstLevelDivisionForSquare(f, cfg, 2, true, bx, by, cx, cy, entropy_mul16X8, entropy_mul16X16, entropy_estimate);
+    }
+    // non-aligned matching for 32X32, 16X32 and 32X16
+    const int step = cfg.speed_tier >= 1 ? 2 : 1;   // kTortoise and faster
+    for (int cy = 0; cy + 3 < rys; cy += step) for (int cx = 0; cx + 3 < rxs; cx += step) {
+      if ((cy | cx) % 4 == 0) continue;   // already tried with the aligned loop
+      FindBestFirstLevelDivisionForSquare(f, cfg, 4, enable_32x32, bx, by, cx, cy, entropy_mul16X32, entropy_mul32X32, entropy_estimate);
+    }
   }
-  float best = cur_h[0] + cur_h[1];
-  int choice = 0;
-  if ((take_h[0] || take_h[1]) && !(cost_h >= best)) { best = cost_h; choice = 1; }
-  if ((take_v[0] || take_v[1]) && !(cost_v >= best)) { best = cost_v; choice = 2; }
-  if (!(e_s >= best)) { best = e_s; choice = 3; }
-  if (choice == 1) {
-    for (int i = 0; i < 2; ++i) if (take_h[i]) SetStrategy(f, s_wide, sx, sy + i * half, e_h[i]);
-  } else if (choice == 2) {
-    for (int i = 0; i < 2; ++i) if (take_v[i]) SetStrategy(f, s_tall, sx + i * half, sy, e_v[i]);
-  } else if (choice == 3) {
-    SetStrategy(f, s_sq, sx, sy, e_s);
-  }
+  for (int iy = 0; iy < rys; ++iy) for (int ix = 0; ix < rxs; ++ix)
+    f->acs_entropy[(size_t)(by + iy) * fd.bxs + bx + ix] = entropy_estimate[iy * 8 + ix];
 }
 
 }  // namespace
@@ -176,41 +406,18 @@ void MergeSquare(Frame* f, const AcsConfig& cfg, int blocks, int sx, int sy) {
 void AcStrategySearch(Frame* f) {
   const FrameDim& fd = f->fd;
   const Params& p = f->params;
-  if (p.effort < 5) return;   // ProcessRectACS returns early for tiers faster than hare (Appendix U.3)
+  if (p.effort < 5) return;   // AcStrategyHeuristics::ProcessRect: DCT8 everywhere at cheetah and faster
   AcsConfig cfg;
   const float ratio = (p.distance + 0.1373f) / 1.1373f;
   cfg.info_loss_multiplier = 1.2f * powf(ratio, 0.33677806662454718f);
   cfg.zeros_mul = 9.3089171683409026f * powf(ratio, 0.50990926717963703f);
   cfg.cost_delta = 10.833273317067883f * powf(ratio, 0.36702940662370243f);
   cfg.distance = p.distance;
+  cfg.speed_tier = 10 - (int)p.effort;
   cfg.partitioning = p.proposal == 1 || p.proposal == 3;
   cfg.factored_entropy = p.proposal == 2 || p.proposal == 3;
-  const float mul8x8 = 1.0f - 0.4f / (p.distance + 1.4f);
-  // ---- FindBest8x8Transform for every block
-  static const int kCand[4] = {DCT, DCT4X4, DCT4X8, DCT8X4};
-  static const float kCandMul[4] = {0.8f, 1.08f, 0.8593f, 0.8593f};
-  for (int by = 0; by < fd.bys; ++by) for (int bx = 0; bx < fd.bxs; ++bx) {
-    float best = 1e30f;
-    int best_tx = DCT;
-    for (int i = 0; i < 4; ++i) {
-      float mul = kCandMul[i] / 0.8f;
-      if (i != 0 && p.distance > 4.0f) mul += 0.5f;     // kAvoidEntropyOfTransforms (diff context :260)
-      const float e = EstimateEntropy(*f, cfg, kCand[i], mul, bx, by);
-      if (e < best) { best = e; best_tx = kCand[i]; }
-    }
-    if (cfg.partitioning && best_tx == DCT) {
-      const float* r = &f->homog[((size_t)by * fd.bxs + bx) * 3];
-      best_tx = HomogeneityPartition(r[0], r[1], r[2], p.distance);
-    }
-    SetStrategy(f, best_tx, bx, by, best * mul8x8);
-  }
-  // ---- merges: aligned 16x16 squares, then aligned 32x32 squares
-  for (int sy = 0; sy + 2 <= fd.bys; sy += 2) for (int sx = 0; sx + 2 <= fd.bxs; sx += 2) MergeSquare(f, cfg, 2, sx, sy);
-  for (int sy = 0; sy + 4 <= fd.bys; sy += 4) for (int sx = 0; sx + 4 <= fd.bxs; sx += 4) {
-    // a half of the square can only be replaced when no existing transform straddles it: after the
-    // 16-level every transform lies inside one 16x16 square, hence inside one half
-    MergeSquare(f, cfg, 4, sx, sy);
-  }
+  for (int ty = 0; ty < fd.tys; ++ty) for (int tx = 0; tx < fd.txs; ++tx)
+    ProcessRectACS(f, cfg, tx * 8, ty * 8, std::min(8, fd.bxs - tx * 8), std::min(8, fd.bys - ty * 8));
 }
 
 }  // namespace jxo

@@ -90,34 +90,38 @@ static void AdjustQuantBlockAC(const float* qm, float scale, int c, float qm_mul
       if (thr[i] < 0.54f) thr[i] = 0.54f;
     }
   }
-  // Block-wide float sums are defined as: per-row partial sums (left to right over the
-  // row's contributing coefficients), then a halving tree over the rows (stride H/2 .. 1),
-  // the association a warp-shuffle butterfly produces (DESIGN.md "Numerics").
+  // Block-wide float sums are defined as per-lane partial sums followed by a halving tree over the lanes
+  // (stride L/2 .. 1), the association a warp-shuffle butterfly produces (DESIGN.md "Numerics").  Lane =
+  // horizontal frequency: the storage row of square / tall transforms (sequential over x), the storage
+  // column of wide ones (sequential over y) — the index a lane of the CUDA path owns after its column pass.
   const int W = xs * 8, H = ys * 8;
-  std::vector<float> r_hf(H, 0.0f), r_err(H, 0.0f), r_vals(H, 0.0f), r_nz[4];
-  for (int i = 0; i < 4; ++i) r_nz[i].assign(H, 0.0f);
+  const bool wide = kCoveredX[strategy] > kCoveredY[strategy];
+  const int L = wide ? W : H;
+  std::vector<float> r_hf(L, 0.0f), r_err(L, 0.0f), r_vals(L, 0.0f), r_nz[4];
+  for (int i = 0; i < 4; ++i) r_nz[i].assign(L, 0.0f);
   float hfMaxErr[4] = {0, 0, 0, 0};
   for (int y = 0; y < H; ++y) {
     for (int x = 0; x < W; ++x) {
       if (x < xs && y < ys) continue;
       const int pos = y * W + x;
+      const int lane = wide ? x : y;
       const int hfix = (y >= H / 2 ? 2 : 0) + (x >= W / 2 ? 1 : 0);
       const float val = in[pos] * (qm[pos] * qac * qm_mul);
       const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
       const float err = fabsf(val - v);
-      r_err[y] += err;
-      r_vals[y] += fabsf(v);
+      r_err[lane] += err;
+      r_vals[lane] += fabsf(v);
       if (c == 1 && v == 0.0f) { if (hfMaxErr[hfix] < err) hfMaxErr[hfix] = err; }
       if (v != 0.0f) {
-        r_nz[hfix][y] += fabsf(v);
+        r_nz[hfix][lane] += fabsf(v);
         const bool in_corner = y >= 7 * ys && x >= 7 * xs;
         const bool on_border = y == H - 1 || x == W - 1;
         const bool in_larger_corner = x >= 4 * xs && y >= 4 * ys;
-        if (in_corner || (on_border && in_larger_corner)) r_hf[y] += fabsf(val);
+        if (in_corner || (on_border && in_larger_corner)) r_hf[lane] += fabsf(val);
       }
     }
   }
-  auto tree = [H](std::vector<float>& p) { for (int st = H / 2; st >= 1; st /= 2) for (int y = 0; y < st; ++y) p[y] = p[y] + p[y + st]; return p[0]; };
+  auto tree = [L](std::vector<float>& p) { for (int st = L / 2; st >= 1; st /= 2) for (int y = 0; y < st; ++y) p[y] = p[y] + p[y + st]; return p[0]; };
   const float sum_hf_rc = tree(r_hf), sum_err = tree(r_err), sum_vals = tree(r_vals);
   float hfNZ[4];
   for (int i = 0; i < 4; ++i) hfNZ[i] = tree(r_nz[i]);

@@ -25,13 +25,13 @@ const uint16_t kCoeffNumNonzeroContext[64] = {
 
 // ------------------------------------------------------------------ fixed-point log2
 static int32_t g_log2_lut[1025];
-static bool g_log2_init = false;
-static void InitLog2() {
+static bool InitLog2() {
   for (int i = 0; i <= 1024; ++i) g_log2_lut[i] = (int32_t)lrint(ldexp(log2(1.0 + (double)i / 1024.0), 20));
-  g_log2_init = true;
+  return true;
 }
 int64_t Log2Q20(uint32_t n) {
-  if (!g_log2_init) InitLog2();
+  static const bool init = InitLog2();   // thread-safe one-time initialisation
+  (void)init;
   const int e = FloorLog2(n);
   const uint32_t m = n << (31 - e);             // leading one at bit 31
   const uint32_t idx = (m >> 21) & 1023;        // next 10 bits

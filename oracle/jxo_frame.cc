@@ -6,8 +6,8 @@
 namespace jxo {
 
 static EncTables* Tables() {
-  static EncTables* t = nullptr;
-  if (!t) { t = new EncTables(); t->Init(); }
+  // (function-local static: initialised once even when the first encodes start on several threads at a time)
+  static EncTables* t = [] { EncTables* p = new EncTables(); p->Init(); return p; }();
   return t;
 }
 

@@ -37,7 +37,7 @@ float FastPow2f(float x) {
   return num / den;
 }
 
-static float FastPowf(float base, float e) { return FastPow2f(FastLog2f(base) * e); }
+float FastPowf(float base, float e) { return FastPow2f(FastLog2f(base) * e); }
 
 static float Mult(float v) { return v > 0.0f ? 1.0f + v : 1.0f / (1.0f - v); }
 
@@ -100,7 +100,19 @@ static const BandParams kDct4x8 = {4, {{2198.050556016380522f, -0.96269623020744
                                        {764.3655248643528689f, -0.92630200888366945f, -0.9675229603596517f, -0.27845290869168118f},
                                        {527.107573587542228f, -1.4594385811273854f, -1.450082094097871593f, -1.5843722511996204f}}};
 
-// kind: DequantMatrices::QuantTable index (0 DCT, 3 DCT4X4, 4 DCT16X16, 5 DCT32X32,
+static const BandParams kDct64 = {8, {{0.9f * 26629.073922049845f, -1.025f, -0.78f, -0.65012f, -0.19041574084286472f, -0.20819395464f, -0.421064f, -0.32733845535848671f},
+                                      {0.9f * 9311.3238710010046f, -0.3041958212306401f, -0.3633036457487539f, -0.35660379990111464f, -0.3443074455424403f, -0.33699592683512467f, -0.30180866526242109f, -0.27321683125358037f},
+                                      {0.9f * 4992.2486445538634f, -1.2f, -1.2f, -0.8f, -0.7f, -0.7f, -0.4f, -0.5f}}};
+static const BandParams kDct32x64 = {8, {{0.65f * 23629.073922049845f, -1.025f, -0.78f, -0.65012f, -0.19041574084286472f, -0.20819395464f, -0.421064f, -0.32733845535848671f},
+                                         {0.65f * 8611.3238710010046f, -0.3041958212306401f, -0.3633036457487539f, -0.35660379990111464f, -0.3443074455424403f, -0.33699592683512467f, -0.30180866526242109f, -0.27321683125358037f},
+                                         {0.65f * 4492.2486445538634f, -1.2f, -1.2f, -0.8f, -0.7f, -0.7f, -0.4f, -0.5f}}};
+// QuantEncoding::Identity / DCT2 parameter sets (per channel)
+static const float kIdWeights[3][3] = {{280.0f, 3160.0f, 3160.0f}, {60.0f, 864.0f, 864.0f}, {18.0f, 200.0f, 200.0f}};
+static const float kDct2Weights[3][6] = {{3840.0f, 2560.0f, 1280.0f, 640.0f, 480.0f, 300.0f},
+                                         {960.0f, 640.0f, 320.0f, 180.0f, 140.0f, 120.0f},
+                                         {640.0f, 320.0f, 128.0f, 64.0f, 32.0f, 16.0f}};
+
+// kind: DequantMatrices::QuantTable index (1 IDENTITY, 2 DCT2X2, 11 DCT64X64, 12 DCT32X64) (0 DCT, 3 DCT4X4, 4 DCT16X16, 5 DCT32X32,
 // 6 DCT8X16, 7 DCT8X32, 8 DCT16X32, 9 DCT4X8).  Weights are laid out like the
 // coefficient block of the kind (long side horizontal).
 int QuantWeights(int kind, std::vector<float>* w) {
@@ -113,6 +125,32 @@ int QuantWeights(int kind, std::vector<float>* w) {
     case 6: bp = &kDct16x8; rows = 8; cols = 16; break;
     case 7: bp = &kDct32x8; rows = 8; cols = 32; break;
     case 8: bp = &kDct32x16; rows = 16; cols = 32; break;
+    case 11: bp = &kDct64; rows = cols = 64; break;
+    case 12: bp = &kDct32x64; rows = 32; cols = 64; break;
+    case 1: {   // IDENTITY: one weight everywhere, two more for positions 1 / 8 and 9
+      w->assign(3 * 64, 0.0f);
+      for (int c = 0; c < 3; ++c) {
+        for (int i = 0; i < 64; ++i) (*w)[c * 64 + i] = kIdWeights[c][0];
+        (*w)[c * 64 + 1] = kIdWeights[c][1];
+        (*w)[c * 64 + 8] = kIdWeights[c][1];
+        (*w)[c * 64 + 9] = kIdWeights[c][2];
+      }
+      return 64;
+    }
+    case 2: {   // DCT2X2: one weight per Hadamard level and orientation
+      w->assign(3 * 64, 0.0f);
+      for (int c = 0; c < 3; ++c) {
+        float* o = &(*w)[c * 64];
+        o[0] = 2989.0f;   // 0xBAD: the DC position is never quantised with this table
+        o[1] = o[8] = kDct2Weights[c][0];
+        o[9] = kDct2Weights[c][1];
+        for (int y = 0; y < 2; ++y) for (int x = 2; x < 4; ++x) { o[y * 8 + x] = kDct2Weights[c][2]; o[x * 8 + y] = kDct2Weights[c][2]; }
+        for (int y = 2; y < 4; ++y) for (int x = 2; x < 4; ++x) o[y * 8 + x] = kDct2Weights[c][3];
+        for (int y = 0; y < 4; ++y) for (int x = 4; x < 8; ++x) { o[y * 8 + x] = kDct2Weights[c][4]; o[x * 8 + y] = kDct2Weights[c][4]; }
+        for (int y = 4; y < 8; ++y) for (int x = 4; x < 8; ++x) o[y * 8 + x] = kDct2Weights[c][5];
+      }
+      return 64;
+    }
     case 3: {
       float w4[3 * 16];
       GetQuantWeights(4, 4, kDct4.b, kDct4.num, w4);

@@ -114,7 +114,7 @@ bool ReconstructRgb(const Frame& f, uint8_t* rgb) {
     }
     for (int c = 0; c < 3; ++c) {
       // lowest frequencies from the DC image (after the chroma-from-luma term used the AC-only Y)
-      float llf[16];
+      float llf[64];
       LowestFrequenciesFromDc(s, &dc[c][(size_t)by * fd.bxs + bx], fd.bxs, llf);
       const int rows = cy * 8, cols = cx * 8;
       const bool transposed = rows >= cols;

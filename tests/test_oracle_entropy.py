@@ -89,11 +89,78 @@ def test_roundtrip_with_search(pkg, oracle, proposal):
         assert np.array_equal(f.dump(st), d.dump(st)), st
     acs = f.dump("acs")
     first = acs[acs >= 128] & 0x7F
-    assert set(np.unique(first)) <= {0, 3, 4, 5, 6, 7, 10, 11, 12, 13}
+    assert set(np.unique(first)) <= {0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 18, 19, 20}
     assert len(set(np.unique(first))) >= 4                     # the search really mixes transform sizes
     base = oracle.encode(img, 1.0, 7, 0, 0).dump("acs")
     if proposal:
         assert not np.array_equal(acs, base)
+
+
+COVERED = {0: (1, 1), 1: (1, 1), 2: (1, 1), 3: (1, 1), 4: (2, 2), 5: (4, 4), 6: (1, 2), 7: (2, 1), 8: (1, 4), 9: (4, 1), 10: (2, 4),
+           11: (4, 2), 12: (1, 1), 13: (1, 1), 18: (8, 8), 19: (4, 8), 20: (8, 4)}   # strategy -> (covered x, covered y)
+
+
+def check_partition(acs, bys, bxs):
+    """Every block is covered by exactly one transform, whose first block carries the 0x80 flag, and no transform leaves
+    its 64x64 tile (libjxl's AcStrategyImage invariants)."""
+    acs = acs.reshape(bys, bxs)
+    seen = np.zeros((bys, bxs), dtype=np.int32)
+    for by in range(bys):
+        for bx in range(bxs):
+            a = int(acs[by, bx])
+            if not a & 0x80:
+                continue
+            cx, cy = COVERED[a & 0x7F]
+            assert by + cy <= bys and bx + cx <= bxs, (bx, by, a)
+            assert (bx % 8) + cx <= 8 and (by % 8) + cy <= 8, (bx, by, a)
+            assert np.all((acs[by:by + cy, bx:bx + cx] & 0x7F) == (a & 0x7F))
+            assert np.count_nonzero(acs[by:by + cy, bx:bx + cx] & 0x80) == 1
+            seen[by:by + cy, bx:bx + cx] += 1
+    assert np.all(seen == 1)
+
+
+@pytest.mark.parametrize("w,h,proposal,effort", [(256, 192, 0, 7), (200, 120, 3, 7), (257, 9, 2, 9), (520, 260, 1, 6), (136, 264, 3, 5)])
+def test_partition_is_valid(pkg, oracle, w, h, proposal, effort):
+    f = oracle.encode(pkg.synth_image(w, h, 40 + proposal), 1.5, effort, proposal, 0)
+    d = oracle.dims(w, h)
+    check_partition(f.dump("acs"), d["bys"], d["bxs"])
+
+
+def test_smooth_content_takes_64_sized_transforms(pkg, oracle):
+    """H10: the 64-level first division (FindBestFirstLevelDivisionForSquare(8, ...), combined.diff context
+    "@@ -911,7 +1144,7") and the TryMergeAcs path for DCT64X32 / DCT32X64 are reachable: a smooth gradient is coded
+    with 64-sized transforms, and the codestream still decodes to what was coded."""
+    yy, xx = np.mgrid[0:256, 0:320]
+    img = np.stack([80 + xx * 0.3 + yy * 0.1, 90 + yy * 0.25, 100 + (xx + yy) * 0.15], axis=-1).astype(np.uint8)
+    f = oracle.encode(img, 2.0, 7, 0, 0)
+    acs = f.dump("acs")
+    first = acs[acs >= 128] & 0x7F
+    assert np.isin(first, (18, 19, 20)).any()
+    d = oracle.dims(320, 256)
+    check_partition(acs, d["bys"], d["bxs"])
+    dec = oracle.decode(f.dump("codestream").tobytes())
+    assert dec.error == "", dec.error
+    for st in LOSSLESS_STAGES:
+        assert np.array_equal(f.dump(st), dec.dump(st)), st
+    rec = oracle.decode_pixels(f.dump("codestream").tobytes(), 320, 256)
+    assert rec is not None and _psnr(rec, img) > 38.0
+
+
+def test_effort_tiers_differ(pkg, oracle):
+    """Efforts the harness sweeps (benchmark.rs:638, 5..=9): hare (5) searches without DCT4X8 / DCT8X4 candidates and
+    without the non-aligned passes; 6..9 run the full search (squirrel / kitten / tortoise do not differ inside the
+    AC-strategy search for step 2 of the non-aligned 32-level pass)."""
+    img = pkg.synth_image(256, 256, 9)
+    a5 = oracle.encode(img, 1.0, 5, 0, 0).dump("acs")
+    a6 = oracle.encode(img, 1.0, 6, 0, 0).dump("acs")
+    a7 = oracle.encode(img, 1.0, 7, 0, 0).dump("acs")
+    first5 = a5[a5 >= 128] & 0x7F
+    assert not np.isin(first5, (12, 13)).any()          # DCT4X8 / DCT8X4 need wombat (effort 6)
+    assert not np.array_equal(a5, a7)
+    assert np.array_equal(a6, a7)
+    # with the partitioning proposal the override can still hand out DCT4X8 / DCT8X4 at effort 5 (the hook has no tier test)
+    p5 = oracle.encode(img, 1.0, 5, 1, 0).dump("acs")
+    assert np.isin(p5[p5 >= 128] & 0x7F, (3, 12, 13)).any()
 
 
 def test_search_effort_gate_and_size(pkg, oracle):
@@ -115,7 +182,7 @@ def test_partition_override_keeps_estimate(pkg, oracle):
     changed = np.flatnonzero(acs0 != acs1)
     # every strategy the partitioning proposal introduces is one of its three outputs or a merge consequence
     assert changed.size > 0
-    assert set(np.unique(acs1[changed] & 0x7F)) <= {0, 3, 12, 13, 4, 5, 6, 7, 10, 11}
+    assert set(np.unique(acs1[changed] & 0x7F)) <= {0, 1, 2, 3, 12, 13, 4, 5, 6, 7, 10, 11, 18, 19, 20}
 
 
 def _psnr(a, b):

@@ -13,3 +13,8 @@ for n in (4, 8, 16, 32):
 for (N, M) in ((16, 2), (32, 4)):
     vals = [1.0 if k == 0 else np.sin(np.pi * k / (2.0 * M)) / ((N // M) * np.sin(np.pi * k / (2.0 * N))) for k in range(M)]
     print(f"static const float kResample{N}_{M}[{M}] = {{" + ", ".join(f(v) for v in vals) + "};")
+# 64-point transforms (round 2): 1/(2 cos((i+1/2) pi / 64)) and the 64 -> 8 resample scales
+vals = [1.0 / (2.0 * np.cos((i + 0.5) * np.pi / 64)) for i in range(32)]
+print("static const float kWc64[32] = {" + ", ".join(f(v) for v in vals) + "};")
+vals = [1.0 if k == 0 else np.sin(np.pi * k / 16.0) / (8 * np.sin(np.pi * k / 128.0)) for k in range(8)]
+print("static const float kResample64_8[8] = {" + ", ".join(f(v) for v in vals) + "};")

@@ -63,6 +63,24 @@ bool Encoder::Init(int device, std::string* err) {
     if (const char* e = getenv("JXLB200_DCT8_ROWS")) dct8_rows_ = atoi(e);
     if (const char* e = getenv("JXLB200_DCT8_TPS")) dct8_tps_ = atoi(e);
   }
+  for (int k = 0; k < 4; ++k) {
+    // coefficient position of (lane, j) in k_acs_evalsq<8> (oracle/jxo_acs.cc LanePosition): DCT, DCT4X4, DCT4X8, DCT8X4
+    std::vector<float> w;
+    host_quant_weights(k == 0 ? 0 : (k == 1 ? 3 : 9), &w);
+    std::vector<float> wl(192), dl(192);
+    for (int c = 0; c < 3; ++c) for (int l = 0; l < 8; ++l) for (int j = 0; j < 8; ++j) {
+      int pos;
+      if (k == 0) pos = l * 8 + j;
+      else if (k == 1) pos = ((j >> 2) + (l & 3) * 2) * 8 + (l >> 2) + (j & 3) * 2;
+      else if (k == 2) pos = ((l >> 2) + (l & 3) * 2) * 8 + j;
+      else pos = ((j >> 2) + (j & 3) * 2) * 8 + l;
+      wl[c * 64 + l * 8 + j] = w[c * 64 + pos];
+      dl[c * 64 + l * 8 + j] = 1.0f / w[c * 64 + pos];
+    }
+    if (!d_w8_[k].Reserve(192) || !d_dq8_[k].Reserve(192)) { *err = "alloc"; return false; }
+    CUDA_OK(cudaMemcpy(d_w8_[k].p, wl.data(), 192 * 4, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(d_dq8_[k].p, dl.data(), 192 * 4, cudaMemcpyHostToDevice));
+  }
   {
     std::vector<uint16_t> order;
     host_natural_order(0, &order);
@@ -130,6 +148,7 @@ void Encoder::Destroy() {
   if (ev_copy_) { cudaEventDestroy(ev_copy_); ev_copy_ = nullptr; }
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); d_weights_t_[k].Release(); d_dequant_t_[k].Release(); }
+  for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 16; ++o) d_inv_order_[o].Release();
@@ -299,6 +318,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   for (int k = 0; k < 17; ++k) {
     tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; tables.wT[k] = d_weights_t_[k].p; tables.dqT[k] = d_dequant_t_[k].p;
   }
+  for (int k = 0; k < 4; ++k) { tables.w8[k] = d_w8_[k].p; tables.dq8[k] = d_dq8_[k].p; }
   if (search) {
     AcsParams ap;
     const float ratio = (p.distance + 0.1373f) / 1.1373f;

@@ -34,7 +34,8 @@ struct AcsParams {
 };
 // quantisation weights / their inverses per table kind; wT / dqT: the same tables transposed ([hf][vf] of the WIDE
 // strategy of kinds 6, 8, 12: the order a lane that owns one horizontal frequency reads them in)
-struct AcsTables { const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; };
+// w8 / dq8: the 8x8 tables of DCT, DCT4X4, DCT4X8, DCT8X4 in the lane order of k_acs_evalsq<8> ([lane][j])
+struct AcsTables { const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; const float* w8[4]; const float* dq8[4]; };
 size_t acs_work_floats(const FrameDim& fd);   // candidate-value tables of the search
 size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-aligned squares (uint32 words)
 void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,

@@ -30,8 +30,8 @@
 //
 // Numerics contract (DESIGN.md "Numerics"): a sum over a transform is defined as per-lane sequential sums
 // followed by an xor-butterfly over the lanes.  Entropy term: lane = horizontal frequency hf, sequential
-// over vf (8x8 special layouts: lane = storage row, sequential over the row).  Loss term: lane = pixel row,
-// sequential over x.
+// over vf (DCT4X4 / DCT4X8 / DCT8X4: the hf of each sub-block column, see storage_index; DCT2X2 / IDENTITY:
+// lane = storage row, sequential over the row).  Loss term: lane = pixel row, sequential over x.
 #include "jxo_frame.h"
 #include "jxo_stages.h"
 
@@ -102,8 +102,12 @@ float EstimateEntropy(const Frame& f, const AcsConfig& cfg, int s, float entropy
   const int lanes = plain ? cols : 8;
   const int per_lane = size / lanes;
   auto storage_index = [&](int lane, int j) {
-    if (!plain) return lane * 8 + j;
-    return rows >= cols ? lane * rows + j : j * cols + lane;   // (hf = lane, vf = j)
+    if (plain) return rows >= cols ? lane * rows + j : j * cols + lane;   // (hf = lane, vf = j)
+    // split 8x8 strategies: the lane that owns horizontal frequency hf of sub-block column q (lane = q * 4 + hf)
+    if (s == DCT4X4) return ((j >> 2) + (lane & 3) * 2) * 8 + (lane >> 2) + (j & 3) * 2;   // j = sub-block row * 4 + vf
+    if (s == DCT4X8) return ((lane >> 2) + (lane & 3) * 2) * 8 + j;                        // j = vf
+    if (s == DCT8X4) return ((j >> 2) + (j & 3) * 2) * 8 + lane;                           // lane = hf, j = half * 4 + vf
+    return lane * 8 + j;                                                                   // DCT2X2, IDENTITY: storage rows
   };
   float entropy = 0.0f, loss_sum = 0.0f;
   for (int c = 0; c < 3; ++c) {

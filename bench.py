@@ -5,10 +5,11 @@ dominant kernel and the CPU baseline beside it.
   python bench.py --gpus N --steps K --warmup W          (N > 1: launched under torchrun)
   python bench.py --impl reference ...                   (CPU arm: the oracle on the host cores)
 
-A step = one batch of `--batch` synthetic images of the workload (BASELINE.json configs[1]:
-3840x2160 RGB8, distance 1.0, fixed DCT8 strategy) per rank, `--pipelines` of them in flight
-(the reference keeps 6 workers busy the same way, benchmark-jpegxl/src/config.rs:22).  `value` is measured with the
-image resident in HBM (jxlb200_encode_device, CUDA events on the encoder's stream);
+A step = one batch of `--batch` synthetic images of the workload per rank, `--pipelines` of them in flight (the
+reference keeps 6 workers busy the same way, benchmark-jpegxl/src/config.rs:22).  The default workload is the
+configuration BASELINE.json's metric is quoted on, configs[4]: 1920x1080 RGB8, combined.diff (both proposals' hooks),
+effort 7, distance 0.5 .. 3.0 round-robin by global image index, image i on rank i mod N.  `value` is measured with the
+images resident in HBM (jxlb200_encode_batch_device, CUDA events on the encoder's streams);
 `e2e` goes through jxlb200_encode with HOST buffers (pinned staging + H2D + kernels + D2H
 of the codestream inside the timed region).  Ranks shard by image (no data-path collective):
 weak scaling; NCCL only gathers the per-rank times.
@@ -44,9 +45,12 @@ WORKLOADS = {
 }
 # algorithmic bytes per pixel of each pipeline stage (DESIGN.md "Kernels")
 STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
-# DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum), per workload kernel;
-# filled from profiles/ (None = not captured for this kernel)
-TRAFFIC_BYTES = {"coeff": 120.4e6}   # profiles/r01f_dct8_v4_recon_full.txt: 100.1 MB read + 20.3 MB written (k_dct8_quant_v4<2, 512>)
+# DRAM bytes of one launch from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum) of the DCT8 frame's
+# transform + quantise kernel at 3840x2160 (profiles/r01f_dct8_v4_recon_full.txt: 100.1 MB read + 20.3 MB written);
+# the search workloads' coefficient stage is a dozen launches (one per strategy), no single capture applies: null
+TRAFFIC_BYTES_K7_DCT8_4K = 120.4e6
+PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9   # issue slots of the GPU: 148 SMs x 4 schedulers x max SM clock
+ACS_WARP_INST_PER_PX = 110.5   # search kernels, warp instructions per pixel at 1080p combined d = 1 (profiles/r02e_inst_1080p.csv)
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -183,7 +187,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     w, h, dist, effort, proposal, flags = WORKLOADS[args.workload]
-    per_step = max(1, min(cores, 8))
+    per_step = max(1, cores)            # one oracle encode per host thread, every core of the box
     cjxl = find_cjxl()
     vals = []
     for i in range(args.warmup + args.steps):
@@ -219,10 +223,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="4k_dct8_d1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="1080p_combined_sweep", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (64: ~24 GP/s, 256: ~28 GP/s — the "
-                    "pipeline's fill and drain, ~4 ms of rANS latency per image, amortise over the step)")
+    ap.add_argument("--no-k7", action="store_true", help="skip the 4K DCT8 sub-record (roofline.k7_dct8)")
+    ap.add_argument("--batch", type=int, default=256, help="images per rank per step (the pipeline's fill and drain, a few ms "
+                    "of rANS latency per image, amortise over the step)")
     ap.add_argument("--pipelines", type=int, default=32, help="images in flight per rank (CUDA streams)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -308,6 +313,34 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- single image through the reference-facing call (host buffer in, codestream out), as the harness calls cjxl
+    single_ms = []
+    for i in range(5):
+        t1 = time.perf_counter()
+        enc.encode(h_imgs[i % n_distinct], distance[i % len(distance)] if isinstance(distance, list) else distance, effort, proposal, flags)
+        single_ms.append((time.perf_counter() - t1) * 1e3)
+    # ---- sub-record: the DCT8-only transform + quantise kernel (K7) and XYB (K1) at 3840x2160, same run
+    k7 = None
+    if rank == 0 and not args.no_k7:
+        img4k = torch.from_numpy(pkg.synth_image(3840, 2160, 7)).cuda()
+        st4 = []
+        for i in range(6):
+            flush.fill_(i & 255)
+            torch.cuda.synchronize()
+            s4 = enc.encode_device(img4k.data_ptr(), 3840, 2160, 3 * 3840, 1.0, 7, 0, 1)
+            if i:
+                st4.append(list(s4.stage_ms))
+        m4 = np.mean(np.array(st4), axis=0)
+        px4 = 3840 * 2160
+        pk, _ = measured_peak_gbs()
+        k7 = {"workload": "4k_dct8_d1 (BASELINE configs[1]), single-image encodes",
+              "kernel": "k_dct8_quant_v4", "kernel_ms": float(m4[STAGE_INDEX["coeff"]]),
+              "achieved": 18.3 * px4 / (float(m4[STAGE_INDEX["coeff"]]) / 1e3) / 1e9, "peak": pk, "unit": "GB/s",
+              "frac": 18.3 * px4 / (float(m4[STAGE_INDEX["coeff"]]) / 1e3) / 1e9 / pk, "traffic": TRAFFIC_BYTES_K7_DCT8_4K,
+              "xyb": {"kernel": "k_rgb8_to_xyb", "kernel_ms": float(m4[STAGE_INDEX["xyb"]]),
+                      "frac": 15.0 * px4 / (float(m4[STAGE_INDEX["xyb"]]) / 1e3) / 1e9 / pk}}
+        del img4k
+
     # per-rank statistics -> job totals (SUM of counters, MAX of times): the only communication of the job
     job = pkg.gather_stats(pkg.ShardStats(images=B * args.steps, pixels=B * args.steps * w * h,
                                           codestream_bytes=out_bytes, device_ms=total_ms, kernel_launches=launches),
@@ -321,7 +354,10 @@ def main():
         e2e_value = world * B * mp * args.steps / e2e_s
         mean_stage = np.mean(np.array(stage_ms), axis=0)
         peak, peak_kind = measured_peak_gbs()
-        # the HBM-bound kernel the north star names: transform + quantise (k_dct8_quant_v4, 18.3 B/px)
+        search = not (flags & 1) and effort >= 5
+        # the HBM-bound stage the north star names: transform + quantise (18.3 B/px: 12 in, 6 out, 0.3 side data).  On
+        # DCT8-only frames that is ONE kernel (k_dct8_quant_v4); on search workloads it is the strategy-binned stage
+        # (k_coeff_lists + k_coeff8<S> + k_coeffsq<N, MODE>, one launch per strategy), timed as a stage.
         dom = "coeff"
         dom_ms = float(mean_stage[STAGE_INDEX[dom]])
         achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -332,8 +368,13 @@ def main():
             t_ms = float(mean_stage[STAGE_INDEX[sname]])
             per_stage[sname] = {"ms": t_ms, "GB/s": bpp_alg * w * h / (t_ms / 1e3) / 1e9 if t_ms > 0 else 0.0,
                                 "frac": (bpp_alg * w * h / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else 0.0}
-        roof = {"bound": "hbm", "kernel": "k_dct8_quant_v4 (transform + quantise)", "achieved": achieved, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES.get(dom),
+        acs_ms = float(mean_stage[STAGE_INDEX["acs"]])
+        roof = {"bound": "hbm",
+                "kernel": ("coefficient stage of the search path: k_coeff_lists + k_coeff8<S> + k_coeffsq<N, MODE> (transform + "
+                           "quantise, one launch per strategy)") if search else "k_dct8_quant_v4 (transform + quantise)",
+                "achieved": achieved, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None if search else (TRAFFIC_BYTES_K7_DCT8_4K if (w, h) == (3840, 2160) else None),
                 "algorithmic_bytes_per_launch": STAGE_BYTES_PER_PX[dom] * w * h, "kernel_ms": dom_ms,
                 "hbm_stages": per_stage,
                 "single_image_stage_ms": {k: float(mean_stage[v]) for k, v in STAGE_INDEX.items()},
@@ -343,11 +384,20 @@ def main():
                                   "ms": float(mean_stage[STAGE_INDEX["ans"]]), "tokens": int(last_stats.num_tokens),
                                   "Mtokens_per_s": (last_stats.num_tokens / 1e6) / (float(mean_stage[STAGE_INDEX["ans"]]) / 1e3)
                                   if mean_stage[STAGE_INDEX["ans"]] > 0 else 0.0,
-                                  "bound": "dependency latency of the longest group's chain (~110 cycles per token, 21 warp "
-                                           "instructions per token; ncu profiles/r01l: fixed-latency waits 43 %, shared-memory "
-                                           "loads 25 %, issue 21 %), not bandwidth"},
-                "note": "per-kernel times from single-image encodes (one stream); the largest stage, the per-group "
-                        "rANS chains (ans), is serial-latency bound, not bandwidth bound: see profiles/"}
+                                  "bound": "dependency latency of the longest group's chain, not bandwidth (profiles/)"},
+                "note": "per-kernel times from single-image encodes (one stream)"}
+        if search:
+            # the stage that dominates the step by time is not a bandwidth stage: the AC-strategy search evaluates ~20
+            # candidate transforms per pixel (FP32-issue bound); reported against the GPU's issue slots
+            inst = ACS_WARP_INST_PER_PX * w * h
+            roof["dominant_by_time"] = {
+                "kernel": "AC-strategy search: k_acs_evalsq<8|16|32|64> + k_acs_eval8s + k_acs_decide", "bound": "fp32 issue",
+                "ms": acs_ms, "warp_instructions": inst, "achieved_Ginst_per_s": inst / (acs_ms / 1e3) / 1e9 if acs_ms > 0 else 0.0,
+                "peak_Ginst_per_s": PEAK_WARP_INST_PER_S / 1e9,
+                "frac": inst / (acs_ms / 1e3) / PEAK_WARP_INST_PER_S if acs_ms > 0 else 0.0,
+                "source": "warp instructions per pixel from ncu smsp__inst_executed.sum (profiles/r02c_inst_1080p.csv)"}
+        if k7 is not None:
+            roof["k7_dct8"] = k7
         line = {
             "metric": "vardct_encode_throughput", "value": value, "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -364,18 +414,21 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": world * B * 3 * w * h,
                     "d2h_bytes_per_step": world * out_bytes // max(1, args.steps), "ms_per_step": e2e_s * 1e3 / args.steps,
-                    "h2d_GBps_per_gpu": B * 3 * w * h / (e2e_s / args.steps) / 1e9,
-                    "note": "bound by the host link: a pinned 256 MiB copy alone reaches 55.5 GB/s on this box"},
+                    "h2d_GBps_per_gpu": B * 3 * w * h / (e2e_s / args.steps) / 1e9},
             "gpu_launches": launches,
             "roofline": roof,
+            "single_image_e2e_ms": float(np.median(single_ms)),
             "bpp": last_stats.bpp, "codestream_bytes": last_stats.codestream_bytes,
             "wall_s_value_loop": wall_s,
         }
-        if not args.no_cpu_baseline and world == 1:
-            cores = 1
-            v, dt = cpu_oracle_throughput(args.workload, 10, 1)
+        if not args.no_cpu_baseline:
+            # rank 0 times the CPU implementation on every host core (one oracle encode per thread), at every N
+            cores = os.cpu_count() or 1
+            n_img = max(cores, 2)
+            v, dt = cpu_oracle_throughput(args.workload, n_img, cores)
             line["cpu_baseline"] = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
-                                    "sample": f"10 images of {w}x{h}, scalar oracle, 1 thread, {dt:.1f} s"}
+                                    "sample": f"{n_img} images of {w}x{h}, one scalar oracle encode per host thread on {cores} "
+                                              f"threads, {dt:.1f} s (own CPU restatement: no libjxl binary exists offline)"}
         print(json.dumps(line), flush=True)
     enc.close()
     if world > 1:

@@ -352,6 +352,17 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
                            d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
+  // (measurement aid, tools/exp_*.py only: JXLB200_DEBUG_SKIP_ENTROPY=1 stops the pipeline here — the output is not a
+  // codestream — to time the front half alone)
+  static const bool skip_entropy = getenv("JXLB200_DEBUG_SKIP_ENTROPY") != nullptr;
+  if (skip_entropy) {
+    for (int i = 7; i <= 12; ++i) CUDA_OK(cudaEventRecord(ev_[i], stream_));
+    CUDA_OK(cudaMemsetAsync(d_out_info_.p, 0, 40 * sizeof(unsigned long long), stream_));
+    CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    launches_ = g_kernel_launches;
+    in_flight_ = true;
+    return true;
+  }
   // K8: tokens + per-context histograms
   CUDA_OK(cudaMemsetAsync(d_hist_.p, 0, (size_t)kNumAcContexts * kAcAlphabet * 4, stream_));
   CUDA_OK(cudaMemsetAsync(d_cluster_hist_.p, 0, kMaxClusters * kAcAlphabet * 4, stream_));

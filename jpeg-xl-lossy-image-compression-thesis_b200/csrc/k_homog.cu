@@ -6,10 +6,15 @@
 // they are a pure function of (block, distance, image), so here they are computed once
 // per 8x8 block: r_h, r_v, r_d.
 //
-// One CTA = 32 horizontally adjacent blocks (256 x 8 px).  Phase 1: one thread per pixel
-// column computes the per-pixel Laplacian and modified-Laplacian terms into shared
-// memory.  Phase 2: one thread per (block, sub-rectangle) accumulates its eight
-// homogeneity values in the reference's sequential order.  Phase 3: ratios.
+// One CTA = 32 horizontally adjacent blocks (256 x 8 px), 256 threads.
+//  phase 1  thread = pixel column: per-pixel Laplacian (only its comparison with the threshold is ever used: one
+//           bit per pixel, gathered into a row mask and a column mask per block) and modified-Laplacian term
+//  phase 2  warp = one of the eight sub-rectangles of CalculateHomogeneitySimilarityIndices, lane = block: the
+//           loop bounds are compile-time constants per warp; zero crossings are counted on the bit masks
+//           (rising edges = m & ~(m << 1)); the float sums run in the reference's sequential order
+//  phase 3  ratios
+// Shared-memory rows carry one pad float per 32 columns (index c + (c >> 5)): the column-per-lane accesses of
+// phase 1 and the block-per-lane (stride 8) accesses of phase 2 are both conflict-free.
 // HBM traffic: 12 B/px in (+ halo re-reads from L2), 12 B/block out.
 #include "jxl_common.cuh"
 #include "kernels.h"
@@ -19,16 +24,70 @@ namespace jxlb {
 __device__ __forceinline__ float hmax(float a, float b) { return (a < b) ? b : a; }  // std::max
 __device__ __forceinline__ float hmin(float a, float b) { return (b < a) ? b : a; }  // std::min
 
+constexpr int kHPitch = 264 + 8;                                     // 258 columns + pads
+__device__ __forceinline__ int hidx(int c) { return c + (c >> 5); }  // padded column index
+
+// one sub-rectangle (XS x YS at (OX, OY) inside the block) of block `cb / 8`: CalculateHomogeneity (diff :153-181)
+template <int XS, int YS, int OX, int OY>
+__device__ __forceinline__ float homogeneity_rect(const float (*ssml)[kHPitch], const float (*sx)[kHPitch], const float (*sb)[kHPitch],
+                                                  const uint8_t* rowmask, const uint8_t* colmask, int cb) {
+  // zero crossings (diff :17-55): rising edges of `laplacian > threshold` along the rows, then along the columns
+  unsigned nh = 0, nv = 0;
+#pragma unroll
+  for (int i = 0; i < YS; ++i) {
+    const unsigned m = ((unsigned)rowmask[OY + i] >> OX) & ((1u << XS) - 1);
+    nh += __popc(m & ~(m << 1));
+  }
+#pragma unroll
+  for (int i = 0; i < XS; ++i) {
+    const unsigned m = ((unsigned)colmask[OX + i] >> OY) & ((1u << YS) - 1);
+    nv += __popc(m & ~(m << 1));
+  }
+  const float avg_h = (float)nh / (float)YS;
+  const float avg_v = (float)nv / (float)XS;
+  const unsigned long long crossings = (unsigned long long)(avg_h + avg_v);
+  // sum modified Laplacian (diff :83-105), colourfulness (diff :107-151): row-major sequential sums
+  float sml = 0.0f, mean_x = 0.0f, mean_b = 0.0f, var_x = 0.0f, var_b = 0.0f;
+  float vx[XS * YS], vb[XS * YS];
+#pragma unroll
+  for (int i = 0; i < YS; ++i)
+#pragma unroll
+    for (int j = 0; j < XS; ++j) {
+      const int c = hidx(cb + OX + j);
+      sml += ssml[OY + i][c];
+      vx[i * XS + j] = sx[OY + i][c];
+      vb[i * XS + j] = sb[OY + i][c];
+    }
+  const float n = (float)(XS * YS);
+#pragma unroll
+  for (int k = 0; k < XS * YS; ++k) mean_x += vx[k];
+  mean_x /= n;
+#pragma unroll
+  for (int k = 0; k < XS * YS; ++k) mean_b += vb[k];
+  mean_b /= n;
+#pragma unroll
+  for (int k = 0; k < XS * YS; ++k) { const float d = vx[k] - mean_x; var_x = __fmaf_rn(d, d, var_x); }
+  var_x /= n;
+#pragma unroll
+  for (int k = 0; k < XS * YS; ++k) { const float d = vb[k] - mean_b; var_b = __fmaf_rn(d, d, var_b); }
+  var_b /= n;
+  const float s1 = var_x + var_b;
+  const float s2 = __fmaf_rn(mean_x, mean_x, mean_b * mean_b);
+  const float col = (float)(sqrt((double)s1) + 0.3 * sqrt((double)s2));
+  return ((float)crossings + sml) + col;
+}
+
 __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X, const float* __restrict__ Y,
                                                      const float* __restrict__ B, FrameDim fd, float distance,
                                                      float* __restrict__ out) {
-  __shared__ float sy[10][260];   // rows -1..8, cols -1..256 (+pad)
-  __shared__ float sx[8][256];
-  __shared__ float sb[8][256];
-  __shared__ float slap[8][256];
-  __shared__ float ssml[8][256];
+  __shared__ float sy[10][kHPitch];   // rows -1..8, columns -1..256 stored at hidx(column + 1)
+  __shared__ float sx[8][kHPitch];
+  __shared__ float sb[8][kHPitch];
+  __shared__ float ssml[8][kHPitch];
+  __shared__ uint8_t sbits[8][256];   // per pixel: laplacian > threshold
+  __shared__ uint8_t srow[32][8], scol[32][8];
   __shared__ float sh[32][8];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int by = blockIdx.y;
   const int px0 = blockIdx.x * 256;
   const int gy0 = by * 8;
@@ -38,24 +97,27 @@ __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X
     const int gy = gy0 + r - 1, gx = px0 + c - 1;
     float v = 0.0f;
     if (gy >= 0 && gy < fd.ys_pad && gx >= 0 && gx < fd.pitch) v = Y[(size_t)gy * fd.pitch + gx];
-    sy[r][c] = v;
+    sy[r][hidx(c)] = v;
   }
   for (int i = t; i < 8 * 256; i += 256) {
     const int r = i >> 8, c = i & 255;
     const int gx = px0 + c;
     float vx = 0.0f, vb = 0.0f;
     if (gx < fd.pitch) { vx = X[(size_t)(gy0 + r) * fd.pitch + gx]; vb = B[(size_t)(gy0 + r) * fd.pitch + gx]; }
-    sx[r][c] = vx; sb[r][c] = vb;
+    sx[r][hidx(c)] = vx; sb[r][hidx(c)] = vb;
   }
   __syncthreads();
+  float thr = 0.25f;
+  if (distance > 10.0f) thr = 0.40f; else if (distance <= 2.0f) thr = 0.15f;
   // ---- phase 1: per-pixel terms, thread = pixel column ---------------------------------
   {
     const int c = t;
     const int gx = px0 + c;
+    const int cl = hidx(c), cm = hidx(c + 1), cr = hidx(c + 2);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int gy = gy0 + r;
-      const float p = sy[r + 1][c + 1], pl = sy[r + 1][c], pr = sy[r + 1][c + 2], pu = sy[r][c + 1], pd = sy[r + 2][c + 1];
+      const float p = sy[r + 1][cm], pl = sy[r + 1][cl], pr = sy[r + 1][cr], pu = sy[r][cm], pd = sy[r + 2][cm];
       // CalculateLaplacianFilter (diff :57-81): mask {{0,-1,0},{-1,-4,-1},{0,-1,0}}, k-major order
       float sum = 0.0f;
       if (gy - 1 >= 0 && gx < fd.pitch) sum = __fmaf_rn(pu, -1.0f, sum);
@@ -63,71 +125,40 @@ __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X
       if (gx < fd.pitch) sum = __fmaf_rn(p, -4.0f, sum);
       if (gx + 1 < fd.pitch) sum = __fmaf_rn(pr, -1.0f, sum);
       if (gy + 1 < fd.ys_pad && gx < fd.pitch) sum = __fmaf_rn(pd, -1.0f, sum);
-      slap[r][c] = sum;
+      sbits[r][c] = sum > thr ? 1 : 0;
       // CalculateSumModifiedLaplacian term (diff :83-105); skipped pixels contribute +0
       float term = 0.0f;
       if (!(gx + 1 >= fd.pitch || gy + 1 >= fd.ys_pad || gx == 0 || gy == 0))
         term = fabsf(2 * p - pl - pr) + fabsf(2 * p - pu - pd);
-      ssml[r][c] = term;
+      ssml[r][cl] = term;
     }
   }
   __syncthreads();
-  // ---- phase 2: thread = (block, sub-rectangle) ---------------------------------------
+  // ---- per block: eight row masks (bit j = column j) and eight column masks (bit i = row i)
   {
-    const int b = t >> 3, sr = t & 7;
-    // (xsize, ysize, bx, by) of the eight calls in CalculateHomogeneitySimilarityIndices
-    const int xs = (sr < 2) ? 8 : 4;
-    const int ys = (sr < 2) ? 4 : ((sr < 4) ? 8 : 4);
-    const int ox = (sr == 3 || sr == 5 || sr == 7) ? 4 : 0;
-    const int oy = (sr == 1 || sr == 5 || sr == 6) ? 4 : 0;
-    const int cb = b * 8;
-    float thr = 0.25f;
-    if (distance > 10.0f) thr = 0.40f; else if (distance <= 2.0f) thr = 0.15f;
-    // zero crossings (diff :17-55)
-    unsigned nh = 0, nv = 0;
-    for (int i = 0; i < ys; ++i) {
-      bool in_edge = false;
-      for (int j = 0; j < xs; ++j) {
-        const float v = slap[oy + i][cb + ox + j];
-        if (!in_edge && v > thr) { nh++; in_edge = true; }
-        else if (in_edge && v <= thr) { in_edge = false; }
-      }
+    const int b = t >> 3, k = t & 7;
+    unsigned rm = 0, cmk = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { rm |= (unsigned)sbits[k][b * 8 + j] << j; cmk |= (unsigned)sbits[j][b * 8 + k] << j; }
+    srow[b][k] = (uint8_t)rm; scol[b][k] = (uint8_t)cmk;
+  }
+  __syncthreads();
+  // ---- phase 2: warp = sub-rectangle of CalculateHomogeneitySimilarityIndices (diff :183-211), lane = block ------
+  {
+    const int cb = lane * 8;
+    const uint8_t* rmk = srow[lane]; const uint8_t* cmk = scol[lane];
+    float h;
+    switch (warp) {   // (xsize, ysize, bx, by) of the eight calls
+      case 0: h = homogeneity_rect<8, 4, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 1: h = homogeneity_rect<8, 4, 0, 4>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 2: h = homogeneity_rect<4, 8, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 3: h = homogeneity_rect<4, 8, 4, 0>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 4: h = homogeneity_rect<4, 4, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 5: h = homogeneity_rect<4, 4, 4, 4>(ssml, sx, sb, rmk, cmk, cb); break;
+      case 6: h = homogeneity_rect<4, 4, 0, 4>(ssml, sx, sb, rmk, cmk, cb); break;
+      default: h = homogeneity_rect<4, 4, 4, 0>(ssml, sx, sb, rmk, cmk, cb); break;
     }
-    for (int i = 0; i < xs; ++i) {
-      bool in_edge = false;
-      for (int j = 0; j < ys; ++j) {
-        const float v = slap[oy + j][cb + ox + i];
-        if (!in_edge && v > thr) { nv++; in_edge = true; }
-        else if (in_edge && v <= thr) { in_edge = false; }
-      }
-    }
-    const float avg_h = (float)nh / (float)ys;
-    const float avg_v = (float)nv / (float)xs;
-    const unsigned long long crossings = (unsigned long long)(avg_h + avg_v);
-    // sum modified Laplacian
-    float sml = 0.0f;
-    for (int i = 0; i < ys; ++i) for (int j = 0; j < xs; ++j) sml += ssml[oy + i][cb + ox + j];
-    // colourfulness (diff :107-151)
-    const float n = (float)(xs * ys);
-    float mean_x = 0.0f, mean_b = 0.0f, var_x = 0.0f, var_b = 0.0f;
-    for (int i = 0; i < ys; ++i) for (int j = 0; j < xs; ++j) mean_x += sx[oy + i][cb + ox + j];
-    mean_x /= n;
-    for (int i = 0; i < ys; ++i) for (int j = 0; j < xs; ++j) mean_b += sb[oy + i][cb + ox + j];
-    mean_b /= n;
-    for (int i = 0; i < ys; ++i) for (int j = 0; j < xs; ++j) {
-      const float d = sx[oy + i][cb + ox + j] - mean_x;
-      var_x = __fmaf_rn(d, d, var_x);
-    }
-    var_x /= n;
-    for (int i = 0; i < ys; ++i) for (int j = 0; j < xs; ++j) {
-      const float d = sb[oy + i][cb + ox + j] - mean_b;
-      var_b = __fmaf_rn(d, d, var_b);
-    }
-    var_b /= n;
-    const float s1 = var_x + var_b;
-    const float s2 = __fmaf_rn(mean_x, mean_x, mean_b * mean_b);
-    const float col = (float)(sqrt((double)s1) + 0.3 * sqrt((double)s2));
-    sh[b][sr] = ((float)crossings + sml) + col;
+    sh[lane][warp] = h;
   }
   __syncthreads();
   // ---- phase 3: similarity indices (diff :183-211) -------------------------------------

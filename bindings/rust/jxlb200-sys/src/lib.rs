@@ -3,7 +3,7 @@
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const JXLB200_ABI_VERSION: c_int = 2;
+pub const JXLB200_ABI_VERSION: c_int = 3;
 
 #[repr(C)]
 pub struct jxlb200_ctx {
@@ -106,5 +106,15 @@ extern "C" {
     pub fn jxlb200_fetch(ctx: *mut jxlb200_ctx, out: *mut *mut u8, out_len: *mut usize) -> c_int;
     pub fn jxlb200_free(buf: *mut c_void);
     pub fn jxlb200_dump(ctx: *mut jxlb200_ctx, stage: c_int, dst: *mut c_void, cap: usize) -> i64;
+    pub fn jxlb200_debug_homogeneity(
+        ctx: *mut jxlb200_ctx,
+        x: *const f32,
+        y: *const f32,
+        b: *const f32,
+        stride: u32,
+        ysize: u32,
+        distance: f32,
+        out: *mut f32,
+    ) -> c_int;
     pub fn jxlb200_dims(width: u32, height: u32, dims: *mut i32);
 }

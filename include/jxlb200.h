@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define JXLB200_ABI_VERSION 2
+#define JXLB200_ABI_VERSION 3
 
 typedef struct jxlb200_ctx jxlb200_ctx;
 
@@ -159,6 +159,14 @@ int jxlb200_set_pipelines(jxlb200_ctx* ctx, int n);
 /* Copies the intermediate `stage` of the LAST encode on this context to host memory.
  * Returns the stage size in bytes (copying only if cap is large enough), or < 0. */
 int64_t jxlb200_dump(jxlb200_ctx* ctx, int stage, void* dst, size_t cap);
+
+/* Parity tap for the reference-pinned rows H1-H7 (proposals/homogeneity-partitioning.diff:17-211): runs the
+ * homogeneity kernel on caller-supplied planar XYB (host memory, `stride` floats per row, `ysize` rows — the
+ * `config.src_stride` / `config.src_ysize` of the diff, :402-421) and returns r_h, r_v, r_d of every 8x8 block,
+ * out[(by * (stride / 8) + bx) * 3 + k].  No counterpart in the reference; it lets the hand-computed vectors of
+ * tests/golden/ reach the CUDA kernel with exactly their inputs. */
+int jxlb200_debug_homogeneity(jxlb200_ctx* ctx, const float* x, const float* y, const float* b, uint32_t stride,
+                              uint32_t ysize, float distance, float* out);
 
 /* Frame geometry helper: dims[16] = xsize ysize xs_pad ys_pad pitch bxs bys gxs gys
  * num_groups dgxs dgys num_dc_groups txs tys 0 */

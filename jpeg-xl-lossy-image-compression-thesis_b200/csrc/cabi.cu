@@ -85,6 +85,8 @@ static int check_params(jxlb200_ctx* ctx, uint32_t w, uint32_t h, const jxlb200_
   if (!p) return fail(ctx, "null params");
   if (w == 0 || h == 0) return fail(ctx, "invalid image");
   if ((uint64_t)w * h > (1ull << 28)) return fail(ctx, "image too large");
+  // several launches put image rows in grid.y (limit 65535): refuse taller images up front instead of failing a launch
+  if (h > 65528u) return fail(ctx, "image taller than 65528 rows is not supported");
   if (!(p->distance >= 0.01f && p->distance <= 25.0f)) return fail(ctx, "distance out of range [0.01, 25]");
   if (p->effort < 1 || p->effort > 9) return fail(ctx, "effort out of range [1, 9]");
   if (p->proposal > 3) return fail(ctx, "unknown proposal");
@@ -251,6 +253,16 @@ int64_t jxlb200_dump(jxlb200_ctx* ctx, int stage, void* dst, size_t cap) {
   const int64_t r = ctx->enc.Dump(stage, dst, cap, &e);
   if (r < 0) ctx->err = e;
   return r;
+}
+
+int jxlb200_debug_homogeneity(jxlb200_ctx* ctx, const float* x, const float* y, const float* b, uint32_t stride, uint32_t ysize,
+                              float distance, float* out) {
+  if (!ctx) return -1;
+  if (!x || !y || !b || !out) return fail(ctx, "null plane");
+  if (stride < 8 || ysize < 8 || stride > 16384 || ysize > 16384) return fail(ctx, "plane size out of range [8, 16384]");
+  std::string e;
+  if (!ctx->enc.DebugHomogeneity(x, y, b, (int)stride, (int)ysize, distance, out, &e)) return fail(ctx, e);
+  return 0;
 }
 
 void jxlb200_dims(uint32_t width, uint32_t height, int32_t* dims) {

@@ -483,6 +483,24 @@ bool Encoder::Fetch(uint8_t** out, size_t* out_len, std::string* err) {
   return true;
 }
 
+bool Encoder::DebugHomogeneity(const float* x, const float* y, const float* b, int stride, int ysize, float distance, float* out,
+                               std::string* err) {
+  CUDA_OK(cudaSetDevice(device_));
+  // geometry exactly as given: the row pitch IS the diff's src_stride bound, ysize its src_ysize (H1)
+  FrameDim fd{};
+  fd.xsize = fd.xs_pad = stride; fd.ysize = fd.ys_pad = ysize; fd.pitch = stride; fd.bxs = stride / 8; fd.bys = ysize / 8;
+  const size_t plane = (size_t)stride * ysize, nblk = (size_t)fd.bxs * fd.bys;
+  DevBuf<float> planes, res;
+  if (!planes.Reserve(3 * plane) || !res.Reserve(3 * nblk + 1)) { *err = "device allocation failed"; return false; }
+  const float* src[3] = {x, y, b};
+  for (int c = 0; c < 3; ++c) CUDA_OK(cudaMemcpyAsync(planes.p + c * plane, src[c], plane * 4, cudaMemcpyHostToDevice, stream_));
+  launch_homogeneity(planes.p, planes.p + plane, planes.p + 2 * plane, fd, distance, res.p, stream_);
+  CUDA_OK(cudaMemcpyAsync(out, res.p, 3 * nblk * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  planes.Release(); res.Release();
+  return true;
+}
+
 int64_t Encoder::Dump(int stage, void* dst, size_t cap, std::string* err) {
   if (!have_frame_) { *err = "no encoded frame"; return -1; }
   cudaSetDevice(device_);
@@ -523,6 +541,45 @@ int64_t Encoder::Dump(int stage, void* dst, size_t cap, std::string* err) {
         for (int g = 0; g < fd.num_groups; ++g)
           if (counts[g] && cudaMemcpy((uint8_t*)dst + (size_t)offs[g] * 4, d_tokens_.p + (size_t)g * kTokensPerGroupMax,
                                       (size_t)counts[g] * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }
+      }
+      return (int64_t)bytes;
+    }
+    case JXLB200_STAGE_GROUP_OFFSETS:
+    case JXLB200_STAGE_GROUP_STREAMS: {
+      // every AC group's rANS stream sits at the END of its arena slot (it is written back to front): bits
+      // [start_bit, slot end).  The tap returns each stream from its first bit, LSB-first, zero-padded to a whole byte
+      // (what the oracle's per-group BitWriter holds), and the byte offsets of the groups.
+      std::vector<unsigned long long> start(fd.num_groups);
+      if (cudaMemcpy(start.data(), d_group_start_.p, start.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }
+      const unsigned long long slot_bits = (unsigned long long)kTokensPerGroupMax * 32;
+      std::vector<uint32_t> offs(fd.num_groups + 1, 0);
+      for (int g = 0; g < fd.num_groups; ++g) offs[g + 1] = offs[g] + (uint32_t)((slot_bits - start[g] + 7) / 8);
+      if (stage == JXLB200_STAGE_GROUP_OFFSETS) {
+        bytes = offs.size() * 4;
+        if (dst && cap >= bytes) memcpy(dst, offs.data(), bytes);
+        return (int64_t)bytes;
+      }
+      bytes = offs.back();
+      if (dst && cap >= bytes) {
+        std::vector<uint32_t> words;
+        for (int g = 0; g < fd.num_groups; ++g) {
+          const size_t w0 = (size_t)(start[g] / 32), nw = (size_t)kTokensPerGroupMax - w0;
+          words.assign(nw + 1, 0u);
+          if (nw && cudaMemcpy(words.data(), d_group_arena_.p + (size_t)g * kTokensPerGroupMax + w0, nw * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { *err = "memcpy"; return -1; }
+          const unsigned sh = (unsigned)(start[g] % 32);
+          const unsigned long long nbits = slot_bits - start[g];
+          uint8_t* o = (uint8_t*)dst + offs[g];
+          for (unsigned long long b = 0; b < nbits; b += 8) {
+            const unsigned long long pos = sh + b;                   // bit position inside `words`
+            const size_t wi = (size_t)(pos / 32);
+            const unsigned bo = (unsigned)(pos % 32);
+            unsigned long long two = (unsigned long long)words[wi] | ((unsigned long long)words[wi + 1] << 32);
+            unsigned v = (unsigned)((two >> bo) & 0xFFu);
+            const unsigned long long left = nbits - b;
+            if (left < 8) v &= (1u << left) - 1u;
+            o[b / 8] = (uint8_t)v;
+          }
+        }
       }
       return (int64_t)bytes;
     }

@@ -40,6 +40,8 @@ class Encoder {
   bool Finish(jxlb200_stats* stats, std::string* err);
   bool Fetch(uint8_t** out, size_t* out_len, std::string* err);
   int64_t Dump(int stage, void* dst, size_t cap, std::string* err);
+  // parity tap: homogeneity map of caller-supplied XYB planes (see jxlb200_debug_homogeneity)
+  bool DebugHomogeneity(const float* x, const float* y, const float* b, int stride, int ysize, float distance, float* out, std::string* err);
   cudaStream_t stream() const { return stream_; }
   // 1 = lowest latency (one group per warp); > 1 packs the rANS chains onto fewer SMs (batch throughput)
   void set_ans_groups_per_warp(int n) { ans_groups_per_warp_ = n; }

@@ -130,6 +130,8 @@ def load_library() -> ctypes.CDLL:
     lib.jxlb200_dump.restype = ctypes.c_int64
     lib.jxlb200_dump.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
     lib.jxlb200_dims.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32)]
+    lib.jxlb200_debug_homogeneity.restype = ctypes.c_int
+    lib.jxlb200_debug_homogeneity.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, vp]
     _LIB = lib
     return lib
 
@@ -266,6 +268,18 @@ class Encoder:
         self._lib.jxlb200_free(out)
         return data
 
+    def homogeneity_map(self, x, y, b, distance: float) -> np.ndarray:
+        """r_h, r_v, r_d of every 8x8 block of caller-supplied XYB planes (rows x stride float32 arrays; the stride is the
+        reference's `src_stride` bound, the row count its `src_ysize`): jxlb200_debug_homogeneity."""
+        x, y, b = (np.ascontiguousarray(a, dtype=np.float32) for a in (x, y, b))
+        rows, stride = y.shape
+        out = np.zeros((rows // 8, stride // 8, 3), dtype=np.float32)
+        rc = self._lib.jxlb200_debug_homogeneity(self._ctx, x.ctypes.data, y.ctypes.data, b.ctypes.data, stride, rows,
+                                                 float(distance), out.ctypes.data)
+        if rc != 0:
+            raise EncodeError(self.last_error())
+        return out
+
     def dump(self, stage) -> np.ndarray:
         """Intermediate of the last encode as a flat numpy array (parity taps)."""
         sid = STAGE_ID[stage] if isinstance(stage, str) else int(stage)
@@ -295,12 +309,21 @@ class Encoder:
 
 
 def _read_image(path: str) -> np.ndarray:
+    """The harness hands PNG paths to cjxl (benchmark.rs:654-660); binary PPM and .npy are accepted as well."""
     if path.endswith(".npy"):
         return np.load(path)
     with open(path, "rb") as f:
         data = f.read()
+    if data[:8] == b"\x89PNG\r\n\x1a\n":
+        try:
+            from PIL import Image
+        except ImportError as e:
+            raise ValueError("PNG input needs Pillow") from e
+        import io
+        with Image.open(io.BytesIO(data)) as im:
+            return np.ascontiguousarray(np.asarray(im.convert("RGB"), dtype=np.uint8))
     if data[:2] != b"P6":
-        raise ValueError("only binary PPM (P6) and .npy inputs are supported")
+        raise ValueError("only PNG, binary PPM (P6) and .npy inputs are supported")
     parts, pos = [], 2
     while len(parts) < 3:
         while data[pos:pos + 1].isspace():

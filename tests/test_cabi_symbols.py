@@ -16,7 +16,7 @@ def test_exports_match_header(pkg):
     lib = ctypes.CDLL(pkg.library_path())
     for n in sorted(names):
         assert hasattr(lib, n), f"{n} declared in include/jxlb200.h but not exported"
-    assert pkg.load_library().jxlb200_abi_version() == 2
+    assert pkg.load_library().jxlb200_abi_version() == 3
 
 
 def test_dims_helper(pkg, oracle):

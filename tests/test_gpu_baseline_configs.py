@@ -1,0 +1,105 @@
+"""GPU parity at BASELINE.json's exact sizes and settings (configs[2..4]) through the C ABI, plus the reference-pinned
+homogeneity vectors (rows H1-H7) run through the CUDA kernel itself, and the per-group stream taps.
+
+The oracle needs ~7 s per 1920x1080 search encode and ~2 min for 7680x4320 on one core, so the oracle encodes of a test
+run side by side on host threads (ctypes releases the GIL)."""
+import base64
+import json
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SWEEP = (0.5, 1.0, 1.5, 2.0, 2.5, 3.0)     # BASELINE configs[4]: "distance sweep 0.5-3.0 (combined.diff)"
+
+
+def test_1080p_combined_at_every_sweep_distance(pkg, oracle, encoder):
+    """configs[4] (one image of the 4096): 1920x1080 (8 x 5 ragged AC groups, 30 x 17 tiles with a ragged last tile row),
+    combined.diff, effort 7, each distance of the sweep: strategy map and codestream equal the oracle's."""
+    img = pkg.synth_image(1920, 1080, 17)
+    with ThreadPoolExecutor(max_workers=len(SWEEP)) as ex:
+        oras = list(ex.map(lambda d: oracle.encode(img, d, 7, 3, 0), SWEEP))
+    sizes = []
+    for d, ora in zip(SWEEP, oras):
+        assert ora.error == ""
+        data, st = encoder.encode(img, d, 7, 3, 0)
+        assert np.array_equal(encoder.dump("acs"), ora.dump("acs")), d
+        assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream")), d
+        assert st.num_groups == 40 and st.num_dc_groups == 1
+        sizes.append(len(data))
+    assert all(a > b for a, b in zip(sizes, sizes[1:]))       # bpp falls along the sweep
+
+
+def test_8k_partitioning_equals_oracle(pkg, oracle, encoder):
+    """configs[2]: 7680x4320 with the homogeneity-partitioning proposal, full search: 12 DC groups, 510 AC groups,
+    8160 tiles.  Strategy map, quantised coefficients' statistics and the codestream equal the oracle's."""
+    img = pkg.synth_image(7680, 4320, 23)
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(oracle.encode, img, 1.0, 7, 1, 0)
+        data, st = encoder.encode(img, 1.0, 7, 1, 0)
+        acs, nz = encoder.dump("acs"), encoder.dump("nzeros")
+        ora = fut.result()
+    assert ora.error == ""
+    assert st.num_dc_groups == 12 and st.num_groups == 510
+    assert np.array_equal(acs, ora.dump("acs"))
+    assert np.array_equal(nz, ora.dump("nzeros"))
+    assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream"))
+    first = acs[acs >= 128] & 0x7F
+    assert np.isin(first, (3, 12, 13)).any() and np.isin(first, (18, 19, 20)).any()   # the override and the 64-level both act
+
+
+def test_1080p_factored_entropy_batch_equals_singles(pkg, encoder):
+    """configs[3]: a batch of 64 1080p images with the factored-entropy proposal through jxlb200_encode_batch equals the
+    64 one-at-a-time encodes (each of which the other tests tie to the oracle)."""
+    imgs = [pkg.synth_image(1920, 1080, 100 + i) for i in range(8)]
+    batch = [imgs[i % 8] for i in range(64)]
+    dists = [SWEEP[i % len(SWEEP)] for i in range(64)]
+    encoder.set_pipelines(16)
+    datas, sts = encoder.encode_batch(batch, dists, 7, 2, 0)
+    encoder.set_pipelines(4)
+    singles = {}
+    for i in range(64):
+        key = (i % 8, dists[i])
+        if key not in singles:
+            singles[key] = encoder.encode(batch[i], dists[i], 7, 2, 0)[0]
+        assert datas[i] == singles[key], i
+        assert sts[i].codestream_bytes == len(datas[i])
+
+
+def _cases():
+    with open(os.path.join(ROOT, "tests", "golden", "homogeneity_cases.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["name"])
+def test_homogeneity_golden_vectors_on_the_gpu(pkg, encoder, case):
+    """rows H1-H7: the hand-computed vectors of tests/golden/ (independent numpy restatement of
+    proposals/homogeneity-partitioning.diff:17-211, tools/make_golden.py) through the CUDA kernel with exactly their
+    planes, stride and ysize (jxlb200_debug_homogeneity).  Tolerance 2e-6 relative: the golden evaluates the final
+    sqrt in float, the diff's `0.3 * sqrt(...)` promotes to double (H5)."""
+    shape = tuple(case["shape"])
+    dec = lambda s: np.frombuffer(base64.b64decode(s), dtype=np.float32).reshape(shape)
+    r = encoder.homogeneity_map(dec(case["X"]), dec(case["Y"]), dec(case["B"]), case["d"])
+    got = r[case["py"] // 8, case["px"] // 8]
+    for g, w in zip(got, case["r"]):
+        if w is None:
+            assert np.isnan(g)
+        elif isinstance(w, str):
+            assert np.isinf(g) and (g > 0) == (w == "inf")
+        else:
+            assert abs(g - w) <= 2e-6 * max(1.0, abs(w)), (got, case["r"])
+
+
+def test_group_stream_taps(pkg, oracle, encoder):
+    """JXLB200_STAGE_GROUP_STREAMS / GROUP_OFFSETS: every AC group's rANS section as the oracle's per-group writer holds it
+    (the north star's "bit-exact group bitstreams")."""
+    for (w, h, flags) in ((520, 260, 0), (264, 300, 1), (1000, 700, 0)):
+        img = pkg.synth_image(w, h, w)
+        encoder.encode(img, 1.0, 7, 3, flags)
+        ora = oracle.encode(img, 1.0, 7, 3, flags)
+        assert np.array_equal(encoder.dump("group_offsets"), ora.dump("group_offsets"))
+        assert np.array_equal(encoder.dump("group_streams"), ora.dump("group_streams"))

@@ -250,11 +250,8 @@ __device__ __forceinline__ int adjust_quant8(const float* cf, const float* __res
 }
 
 template <int S>
-__global__ void __launch_bounds__(64) k_coeff8(CoeffArgs A) {
+__device__ __noinline__ void coeff8_body(const CoeffArgs& A, unsigned i) {
   const FrameDim& fd = A.fd;
-  const unsigned n = *A.count;
-  const unsigned i = blockIdx.x * 64 + threadIdx.x;
-  if (i >= n) return;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   const size_t bi = A.list[i];
   const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
@@ -438,24 +435,22 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
 
 template <int N> struct CoeffSqGeom {
   static constexpr int kGroupsPerWarp = N == 16 ? 2 : 1;
-  static constexpr int kThreads = N == 64 ? 64 : 128;
-  static constexpr int kUnits = N == 64 ? 1 : 4;
-  static constexpr int kGroups = kUnits * kGroupsPerWarp;
+  static constexpr int kThreads = 128;
+  static constexpr int kGroups = N == 64 ? 2 : 4 * kGroupsPerWarp;           // transforms per CTA pass
   static constexpr int kSq = N == 16 ? 256 + 16 : N * N;                    // one square buffer (16: skewed)
   static constexpr int kGroupFloats = 3 * kSq + 3 * 64 + 7 * 64;            // transposition square, X / B stash, LLF, exchange
   static constexpr int kSmemFloats = kGroups * kGroupFloats;
 };
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(CoeffSqGeom<N>::kThreads) k_coeffsq(CoeffArgs A) {
+__device__ __noinline__ void coeffsq_body(const CoeffArgs& A, float* smem_f, unsigned item0) {
   using G = CoeffGeom<N, MODE>;
   using CG = CoeffSqGeom<N>;
   using SX = SquareXform<N>;
-  extern __shared__ __align__(16) float smem_f[];
   const FrameDim& fd = A.fd;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int l = N == 64 ? tid : (lane & (N - 1));
-  const int grp = N == 64 ? 0 : warp * CG::kGroupsPerWarp + (N == 16 ? (lane >> 4) : 0);
+  const int l = N == 64 ? (tid & 63) : (lane & (N - 1));
+  const int grp = N == 64 ? (tid >> 6) : warp * CG::kGroupsPerWarp + (N == 16 ? (lane >> 4) : 0);
   float* base = smem_f + grp * CG::kGroupFloats;
   float* tbuf = base; float* stash[2] = {base + CG::kSq, base + 2 * CG::kSq};
   float* llf = base + 3 * CG::kSq;          // [c][64]
@@ -465,8 +460,8 @@ __global__ void __launch_bounds__(CoeffSqGeom<N>::kThreads) k_coeffsq(CoeffArgs 
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
   const bool owner = l < G::LANES;
-  constexpr int bar_id = 1;
-  for (unsigned item0 = blockIdx.x * CG::kGroups; item0 < n; item0 += gridDim.x * CG::kGroups) {
+  const int bar_id = 1 + grp;   // (N = 64: each pair of warps meets at its own named barrier)
+  {
     const unsigned item = item0 + grp;
     const bool active = item < n;
     const size_t bi = active ? A.list[item] : 0;
@@ -616,34 +611,83 @@ __global__ void __launch_bounds__(CoeffSqGeom<N>::kThreads) k_coeffsq(CoeffArgs 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ host side
-template <int S>
-static void launch_coeff8(CoeffArgs A, int list_id, int kind, uint32_t* lists, const AcsTables& T, size_t nblk, cudaStream_t s) {
-  A.w = T.w[kind]; A.dq = T.dq[kind]; A.inv = nullptr;
-  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
-  ++g_kernel_launches;
-  k_coeff8<S><<<(unsigned)((nblk + 63) / 64), 64, 0, s>>>(A);
-}
-template <int N, int MODE>
-static void launch_coeffsq(CoeffArgs A, int list_id, const float* w, const float* dq, const uint16_t* inv, uint32_t* lists, size_t nblk,
-                           cudaStream_t s) {
-  using CG = CoeffSqGeom<N>;
-  A.w = w; A.dq = dq; A.inv = inv;
-  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
-  const size_t smem = CG::kSmemFloats * sizeof(float);
-  cudaFuncSetAttribute(k_coeffsq<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const size_t max_items = nblk / (size_t)CoeffGeom<N, MODE>::ncov + 1;
-  size_t grid = (max_items + CG::kGroups - 1) / CG::kGroups;
-  if (grid > 148 * 8) grid = 148 * 8;
-  ++g_kernel_launches;
-  k_coeffsq<N, MODE><<<(unsigned)grid, CG::kThreads, smem, s>>>(A);
+// ------------------------------------------------------------------------------------------------ kernels
+// One launch covers all the lists of a size class: a CTA walks "virtual CTAs" (list, chunk of the list), so the
+// strategies of a frame are transformed side by side instead of one short launch after the other.
+struct CoeffAllArgs {
+  CoeffArgs base;                                   // everything but the per-list fields
+  const float* w[kNumLists]; const float* dq[kNumLists]; const uint16_t* inv[kNumLists];
+  const uint32_t* lists;                            // [16 counters][kNumLists][nblk]
+  unsigned nblk;
+};
+
+__device__ __forceinline__ CoeffArgs list_args(const CoeffAllArgs& AA, int li) {
+  CoeffArgs A = AA.base;
+  A.w = AA.w[li]; A.dq = AA.dq[li]; A.inv = AA.inv[li];
+  A.count = AA.lists + li; A.list = AA.lists + 16 + (size_t)li * AA.nblk;
+  return A;
 }
 
+__global__ void __launch_bounds__(64) k_coeff8_all(CoeffAllArgs AA) {
+  unsigned ctas[6], total = 0;
+#pragma unroll
+  for (int li = 0; li < 6; ++li) { ctas[li] = (AA.lists[li] + 63) / 64; total += ctas[li]; }
+  for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
+    unsigned rel = v;
+    int li = 0;
+    while (rel >= ctas[li]) { rel -= ctas[li]; ++li; }
+    const unsigned i = rel * 64 + threadIdx.x;
+    if (i >= AA.lists[li]) continue;
+    const CoeffArgs A = list_args(AA, li);
+    switch (li) {
+      case kListDCT: coeff8_body<kStratDCT>(A, i); break;
+      case kListID: coeff8_body<kStratIDENTITY>(A, i); break;
+      case kList2X2: coeff8_body<kStratDCT2X2>(A, i); break;
+      case kList4X4: coeff8_body<kStratDCT4X4>(A, i); break;
+      case kList4X8: coeff8_body<kStratDCT4X8>(A, i); break;
+      default: coeff8_body<kStratDCT8X4>(A, i); break;
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) k_coeffsq_all(CoeffAllArgs AA) {
+  using CG = CoeffSqGeom<N>;
+  extern __shared__ __align__(16) float smem_f[];
+  constexpr int first = N == 16 ? kList16Tall : (N == 32 ? kList32Tall : kList64Tall);   // tall, wide, square
+  unsigned ctas[3], total = 0;
+#pragma unroll
+  for (int m = 0; m < 3; ++m) { ctas[m] = (AA.lists[first + m] + CG::kGroups - 1) / CG::kGroups; total += ctas[m]; }
+  for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
+    unsigned rel = v;
+    int m = 0;
+    while (rel >= ctas[m]) { rel -= ctas[m]; ++m; }
+    const CoeffArgs A = list_args(AA, first + m);
+    if (m == 0) coeffsq_body<N, kModeTall2>(A, smem_f, rel * CG::kGroups);
+    else if (m == 1) coeffsq_body<N, kModeWide2>(A, smem_f, rel * CG::kGroups);
+    else coeffsq_body<N, kModeSq>(A, smem_f, rel * CG::kGroups);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
 void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s) {
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   cudaMemsetAsync(lists, 0, 64, s);
   ++g_kernel_launches;
   k_coeff_lists<<<(unsigned)((nblk + 255) / 256), 256, 0, s>>>(acs, (int)nblk, lists);
+}
+
+template <int N>
+static void launch_coeffsq_all(const CoeffAllArgs& AA, cudaStream_t s) {
+  using CG = CoeffSqGeom<N>;
+  const size_t smem = CG::kSmemFloats * sizeof(float);
+  cudaFuncSetAttribute(k_coeffsq_all<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t max_items = (size_t)AA.nblk / (N * N / 128) + 3;          // the smallest transforms of the class are N x N/2
+  size_t grid = (max_items + CG::kGroups - 1) / CG::kGroups;
+  if (grid > 148 * 8) grid = 148 * 8;
+  ++g_kernel_launches;
+  k_coeffsq_all<N><<<(unsigned)grid, 128, smem, s>>>(AA);
 }
 
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
@@ -653,26 +697,31 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   cudaMemsetAsync(coeffs, 0, (size_t)fd.num_groups * kGroupBlocks * 192 * sizeof(int16_t), s);
   launch_coeff_lists(acs, fd, lists, s);
-  CoeffArgs A;
+  CoeffAllArgs AA;
+  CoeffArgs& A = AA.base;
   A.X = x; A.Y = y; A.B = b; A.fd = fd; A.qd = qd; A.cmap = cmap; A.x_qm_mul = x_qm_mul; A.b_qm_mul = b_qm_mul; A.adjust = adjust;
   A.raw_qf = raw_qf; A.coeffs = coeffs; A.dc_quant = dc_quant; A.nzeros = nzeros; A.nzcount = nzcount; A.lastk = lastk;
   A.w = nullptr; A.dq = nullptr; A.inv = nullptr; A.list = nullptr; A.count = nullptr;
-  launch_coeff8<kStratDCT>(A, kListDCT, 0, lists, T, nblk, s);
-  launch_coeff8<kStratIDENTITY>(A, kListID, 1, lists, T, nblk, s);
-  launch_coeff8<kStratDCT2X2>(A, kList2X2, 2, lists, T, nblk, s);
-  launch_coeff8<kStratDCT4X4>(A, kList4X4, 3, lists, T, nblk, s);
-  launch_coeff8<kStratDCT4X8>(A, kList4X8, 9, lists, T, nblk, s);
-  launch_coeff8<kStratDCT8X4>(A, kList8X4, 9, lists, T, nblk, s);
-  // inv_order: [order class] natural, [13 + k] transposed for the wide strategy of order class 4 / 6 / 8
-  launch_coeffsq<16, kModeTall2>(A, kList16Tall, T.w[6], T.dq[6], inv_order[4], lists, nblk, s);
-  launch_coeffsq<16, kModeWide2>(A, kList16Wide, T.wT[6], T.dqT[6], inv_order[13], lists, nblk, s);
-  launch_coeffsq<16, kModeSq>(A, kList16Sq, T.w[4], T.dq[4], inv_order[2], lists, nblk, s);
-  launch_coeffsq<32, kModeTall2>(A, kList32Tall, T.w[8], T.dq[8], inv_order[6], lists, nblk, s);
-  launch_coeffsq<32, kModeWide2>(A, kList32Wide, T.wT[8], T.dqT[8], inv_order[14], lists, nblk, s);
-  launch_coeffsq<32, kModeSq>(A, kList32Sq, T.w[5], T.dq[5], inv_order[3], lists, nblk, s);
-  launch_coeffsq<64, kModeTall2>(A, kList64Tall, T.w[12], T.dq[12], inv_order[8], lists, nblk, s);
-  launch_coeffsq<64, kModeWide2>(A, kList64Wide, T.wT[12], T.dqT[12], inv_order[15], lists, nblk, s);
-  launch_coeffsq<64, kModeSq>(A, kList64Sq, T.w[11], T.dq[11], inv_order[7], lists, nblk, s);
+  AA.lists = lists; AA.nblk = (unsigned)nblk;
+  // tables in lane order per list; inv_order: [order class] natural, [13..15] transposed for the wide strategy of class 4 / 6 / 8
+  const int kind8[6] = {0, 1, 2, 3, 9, 9};
+  for (int li = 0; li < 6; ++li) { AA.w[li] = T.w[kind8[li]]; AA.dq[li] = T.dq[kind8[li]]; AA.inv[li] = nullptr; }
+  AA.w[kList16Tall] = T.w[6]; AA.dq[kList16Tall] = T.dq[6]; AA.inv[kList16Tall] = inv_order[4];
+  AA.w[kList16Wide] = T.wT[6]; AA.dq[kList16Wide] = T.dqT[6]; AA.inv[kList16Wide] = inv_order[13];
+  AA.w[kList16Sq] = T.w[4]; AA.dq[kList16Sq] = T.dq[4]; AA.inv[kList16Sq] = inv_order[2];
+  AA.w[kList32Tall] = T.w[8]; AA.dq[kList32Tall] = T.dq[8]; AA.inv[kList32Tall] = inv_order[6];
+  AA.w[kList32Wide] = T.wT[8]; AA.dq[kList32Wide] = T.dqT[8]; AA.inv[kList32Wide] = inv_order[14];
+  AA.w[kList32Sq] = T.w[5]; AA.dq[kList32Sq] = T.dq[5]; AA.inv[kList32Sq] = inv_order[3];
+  AA.w[kList64Tall] = T.w[12]; AA.dq[kList64Tall] = T.dq[12]; AA.inv[kList64Tall] = inv_order[8];
+  AA.w[kList64Wide] = T.wT[12]; AA.dq[kList64Wide] = T.dqT[12]; AA.inv[kList64Wide] = inv_order[15];
+  AA.w[kList64Sq] = T.w[11]; AA.dq[kList64Sq] = T.dq[11]; AA.inv[kList64Sq] = inv_order[7];
+  ++g_kernel_launches;
+  size_t g8 = (nblk + 63) / 64 + 6;
+  if (g8 > 148 * 16) g8 = 148 * 16;
+  k_coeff8_all<<<(unsigned)g8, 64, 0, s>>>(AA);
+  launch_coeffsq_all<64>(AA, s);     // (longest dependency chains first)
+  launch_coeffsq_all<32>(AA, s);
+  launch_coeffsq_all<16>(AA, s);
 }
 
 }  // namespace jxlb

@@ -13,11 +13,17 @@ pub use sys::{
 /// What the device already knows after an encode (the harness derives bpp as 24 / raw_file_size_ratio,
 /// benchmark.rs:921; PSNR as calculate_psnr, image_reader.rs:604-606).
 #[derive(Clone, Copy, Debug)]
+/// What `execute_cjxl_with_stats` reports next to the text line.
+#[derive(Debug, Clone)]
+pub struct EncodeStatsFull { pub codestream_bytes: u64, pub bpp: f64, pub total_ms: f32, pub width: u32, pub height: u32 }
+
 pub struct EncodeStats {
     pub codestream_bytes: u64,
     pub bpp: f64,
     pub device_ms: f32,
     pub psnr: Option<f64>,
+    pub width: u32,
+    pub height: u32,
 }
 
 /// One per worker thread, like each worker's `DockerManager` clone (benchmark.rs:97-103).  A context is owned by
@@ -75,7 +81,23 @@ impl B200Encoder {
         unsafe { sys::jxlb200_free(out as *mut _) };
         let s = unsafe { stats.assume_init() };
         let psnr = if s.quality_valid != 0 { Some(s.psnr) } else { None };
-        Ok((bytes, EncodeStats { codestream_bytes: s.codestream_bytes, bpp: s.bpp, device_ms: s.total_ms, psnr }))
+        Ok((bytes, EncodeStats { codestream_bytes: s.codestream_bytes, bpp: s.bpp, device_ms: s.total_ms, psnr, width, height }))
+    }
+
+    /// `execute_cjxl` that also hands back the statistics (used by the harness' `trait Encoder`,
+    /// bindings/rust/harness/encoder_trait.rs, to fill the bpp / MP/s columns of comparisons.csv).
+    pub fn execute_cjxl_with_stats(&self, input_file: String, output_file: String, distance: f64, effort: u32)
+        -> Result<Result<(String, EncodeStatsFull), String>, Box<dyn Error>> {
+        let img = image::open(&input_file)?.to_rgb8();
+        let (w, h) = img.dimensions();
+        match self.encode_rgb8(img.as_raw(), w, h, distance as f32, effort) {
+            Err(msg) => Ok(Err(msg)),
+            Ok((bytes, s)) => {
+                std::fs::write(&output_file, &bytes)?;
+                let text = format!("Compressed to {} bytes ({:.3} bpp) in {:.3} ms", s.codestream_bytes, s.bpp, s.device_ms);
+                Ok(Ok((text, EncodeStatsFull { codestream_bytes: s.codestream_bytes, bpp: s.bpp, total_ms: s.device_ms, width: w, height: h })))
+            }
+        }
     }
 
     /// Same contract as `DockerManager::execute_cjxl` (docker_manager.rs:100-106): `Ok(Ok(stdout))` on success,

@@ -59,6 +59,7 @@ pub const JXLB200_PROPOSAL_COMBINED: u32 = 3; // proposals/combined.diff
 pub const JXLB200_FLAG_FIXED_DCT8: u32 = 1;
 pub const JXLB200_FLAG_UNIFORM_QF: u32 = 2;
 pub const JXLB200_FLAG_QUALITY: u32 = 4;
+pub const JXLB200_FLAG_FORCED_ACS: u32 = 8;
 
 extern "C" {
     pub fn jxlb200_abi_version() -> c_int;
@@ -106,6 +107,7 @@ extern "C" {
     pub fn jxlb200_fetch(ctx: *mut jxlb200_ctx, out: *mut *mut u8, out_len: *mut usize) -> c_int;
     pub fn jxlb200_free(buf: *mut c_void);
     pub fn jxlb200_dump(ctx: *mut jxlb200_ctx, stage: c_int, dst: *mut c_void, cap: usize) -> i64;
+    pub fn jxlb200_debug_set_strategy_map(ctx: *mut jxlb200_ctx, acs: *const u8, bxs: u32, bys: u32) -> c_int;
     pub fn jxlb200_debug_homogeneity(
         ctx: *mut jxlb200_ctx,
         x: *const f32,

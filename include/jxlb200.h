@@ -46,6 +46,7 @@ enum {
 /* flags */
 #define JXLB200_FLAG_FIXED_DCT8 1u /* skip the AC-strategy search: DCT8 everywhere (BASELINE config 2) */
 #define JXLB200_FLAG_UNIFORM_QF 2u /* skip the adaptive quant field: qf = 0.841/distance everywhere   */
+#define JXLB200_FLAG_FORCED_ACS 8u /* use the map of jxlb200_debug_set_strategy_map instead of the search (jxlb200_encode only)  */
 #define JXLB200_FLAG_QUALITY 4u    /* also reconstruct the coded frame on the device and fill stats.sse / stats.psnr  */
 
 /* Input image: 8-bit sRGB, interleaved RGB, row-major (what the harness hands to cjxl
@@ -159,6 +160,13 @@ int jxlb200_set_pipelines(jxlb200_ctx* ctx, int n);
 /* Copies the intermediate `stage` of the LAST encode on this context to host memory.
  * Returns the stage size in bytes (copying only if cap is large enough), or < 0. */
 int64_t jxlb200_dump(jxlb200_ctx* ctx, int stage, void* dst, size_t cap);
+
+/* Parity tap for row U5: the AC-strategy map (bys x bxs bytes, raw strategy | 0x80 on the first block of every transform:
+ * the layout of JXLB200_STAGE_ACS) that the next jxlb200_encode / jxlb200_encode_device calls with JXLB200_FLAG_FORCED_ACS
+ * code with, instead of searching.  It must be a partition into DCT, IDENTITY, DCT2X2, DCT4X4, DCT4X8, DCT8X4, 16X8, 8X16,
+ * 16X16, 32X8, 8X32, 32X16, 16X32, 32X32, 64X32, 32X64, 64X64 transforms inside their 64x64 tiles.  It reaches the transforms
+ * the search seldom or never picks (libjxl's merge table does not propose DCT32X8 / DCT8X32). */
+int jxlb200_debug_set_strategy_map(jxlb200_ctx* ctx, const uint8_t* acs, uint32_t bxs, uint32_t bys);
 
 /* Parity tap for the reference-pinned rows H1-H7 (proposals/homogeneity-partitioning.diff:17-211): runs the
  * homogeneity kernel on caller-supplied planar XYB (host memory, `stride` floats per row, `ysize` rows — the

@@ -255,6 +255,14 @@ int64_t jxlb200_dump(jxlb200_ctx* ctx, int stage, void* dst, size_t cap) {
   return r;
 }
 
+int jxlb200_debug_set_strategy_map(jxlb200_ctx* ctx, const uint8_t* acs, uint32_t bxs, uint32_t bys) {
+  if (!ctx) return -1;
+  if (!acs || bxs == 0 || bys == 0 || (uint64_t)bxs * bys > (1ull << 22)) return fail(ctx, "invalid strategy map");
+  std::string e;
+  if (!ctx->enc.SetForcedAcs(acs, (int)bxs, (int)bys, &e)) return fail(ctx, e);
+  return 0;
+}
+
 int jxlb200_debug_homogeneity(jxlb200_ctx* ctx, const float* x, const float* y, const float* b, uint32_t stride, uint32_t ysize,
                               float distance, float* out) {
   if (!ctx) return -1;

@@ -46,9 +46,9 @@ bool Encoder::Init(int device, std::string* err) {
     if (!d_weights_[k].Reserve(w.size()) || !d_dequant_[k].Reserve(w.size())) { *err = "alloc"; return false; }
     CUDA_OK(cudaMemcpy(d_weights_[k].p, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(d_dequant_[k].p, dq.data(), dq.size() * 4, cudaMemcpyHostToDevice));
-    if (k == 6 || k == 8 || k == 12) {
+    if (k == 6 || k == 7 || k == 8 || k == 12) {
       // lane order of the WIDE strategy of the kind: [c][hf][vf] (the stored table is [c][vf][hf], H rows of W)
-      const size_t W = k == 6 ? 16 : (k == 8 ? 32 : 64), H = W / 2;
+      const size_t W = k == 6 ? 16 : (k == 12 ? 64 : 32), H = k == 7 ? 8 : W / 2;
       std::vector<float> wt(w.size()), dt(w.size());
       for (size_t c = 0; c < 3; ++c) for (size_t y = 0; y < H; ++y) for (size_t x = 0; x < W; ++x) {
         wt[c * W * H + x * H + y] = w[c * W * H + y * W + x];
@@ -122,11 +122,11 @@ bool Encoder::Init(int device, std::string* err) {
       for (size_t k = 0; k < order.size(); ++k) inv[order[k]] = (uint16_t)k;
       if (!d_inv_order_[o].Reserve(inv.size())) { *err = "alloc"; return false; }
       CUDA_OK(cudaMemcpy(d_inv_order_[o].p, inv.data(), inv.size() * 2, cudaMemcpyHostToDevice));
-      if (o == 4 || o == 6 || o == 8) {   // wide strategy of the class: positions in [hf][vf] lane order
-        const size_t W = o == 4 ? 16 : (o == 6 ? 32 : 64), H = W / 2;
+      if (o == 4 || o == 5 || o == 6 || o == 8) {   // wide strategy of the class: positions in [hf][vf] lane order
+        const size_t W = o == 4 ? 16 : (o == 8 ? 64 : 32), H = o == 5 ? 8 : W / 2;
         std::vector<uint16_t> invt(inv.size());
         for (size_t y = 0; y < H; ++y) for (size_t x = 0; x < W; ++x) invt[x * H + y] = inv[y * W + x];
-        const int slot = o == 4 ? 13 : (o == 6 ? 14 : 15);
+        const int slot = o == 4 ? 13 : (o == 6 ? 14 : (o == 8 ? 15 : 16));
         if (!d_inv_order_[slot].Reserve(invt.size())) { *err = "alloc"; return false; }
         CUDA_OK(cudaMemcpy(d_inv_order_[slot].p, invt.data(), invt.size() * 2, cudaMemcpyHostToDevice));
       }
@@ -151,7 +151,7 @@ void Encoder::Destroy() {
   for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
-  for (int o = 0; o < 16; ++o) d_inv_order_[o].Release();
+  for (int o = 0; o < 17; ++o) d_inv_order_[o].Release();
   d_rgb_.Release(); d_xyb_.Release(); d_mask1x1_.Release(); d_pre_.Release(); d_qf_.Release(); d_mask_.Release();
   d_homog_.Release(); d_acs_entropy_.Release(); d_acs_.Release(); d_raw_qf_.Release(); d_cmap_.Release();
   d_coeffs_.Release(); d_dc_quant_.Release(); d_nzeros_.Release(); d_nzcount_.Release(); d_lastk_.Release(); d_q_.Release();
@@ -312,14 +312,20 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   else CUDA_OK(cudaMemsetAsync(d_homog_.p, 0, 3 * nblk * 4, stream_));
   CUDA_OK(cudaEventRecord(ev_[4], stream_));
   // K6: AC strategy search (+ the proposals' hooks); DCT8 everywhere when fixed or below effort 5
-  const bool search = !(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5;
+  const bool forced = (p.flags & JXLB200_FLAG_FORCED_ACS) != 0;
+  if (forced && (forced_bxs_ != fd.bxs || forced_bys_ != fd.bys)) { *err = "JXLB200_FLAG_FORCED_ACS without a strategy map of this frame's size"; return false; }
+  // `search` selects the general coefficient path (every strategy); the forced map takes it too
+  const bool search = forced || (!(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5);
   CUDA_OK(cudaMemsetAsync(d_cmap_.p, 0, (size_t)2 * fd.txs * fd.tys, stream_));
   AcsTables tables;
   for (int k = 0; k < 17; ++k) {
     tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; tables.wT[k] = d_weights_t_[k].p; tables.dqT[k] = d_dequant_t_[k].p;
   }
   for (int k = 0; k < 4; ++k) { tables.w8[k] = d_w8_[k].p; tables.dq8[k] = d_dq8_[k].p; }
-  if (search) {
+  if (forced) {
+    CUDA_OK(cudaMemcpyAsync(d_acs_.p, forced_acs_.data(), nblk, cudaMemcpyHostToDevice, stream_));
+    CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));
+  } else if (search) {
     AcsParams ap;
     const float ratio = (p.distance + 0.1373f) / 1.1373f;
     ap.info_loss_multiplier = 1.2f * powf(ratio, 0.33677806662454718f);
@@ -341,8 +347,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   CUDA_OK(cudaEventRecord(ev_[5], stream_));
   // K7: transform + quantise
   if (search) {
-    const uint16_t* inv_order[16];
-    for (int o = 0; o < 16; ++o) inv_order[o] = d_inv_order_[o].p;
+    const uint16_t* inv_order[17];
+    for (int o = 0; o < 17; ++o) inv_order[o] = d_inv_order_[o].p;
     launch_coeff_general(X, Y, B, d_acs_.p, fd, d_q_.p, tables, inv_order, d_cmap_.p, x_qm_mul_, b_qm_mul_,
                          p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
                          d_coeff_lists_.p, stream_);
@@ -352,17 +358,6 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
                            d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
-  // (measurement aid, tools/exp_*.py only: JXLB200_DEBUG_SKIP_ENTROPY=1 stops the pipeline here — the output is not a
-  // codestream — to time the front half alone)
-  static const bool skip_entropy = getenv("JXLB200_DEBUG_SKIP_ENTROPY") != nullptr;
-  if (skip_entropy) {
-    for (int i = 7; i <= 12; ++i) CUDA_OK(cudaEventRecord(ev_[i], stream_));
-    CUDA_OK(cudaMemsetAsync(d_out_info_.p, 0, 40 * sizeof(unsigned long long), stream_));
-    CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
-    launches_ = g_kernel_launches;
-    in_flight_ = true;
-    return true;
-  }
   // K8: tokens + per-context histograms
   CUDA_OK(cudaMemsetAsync(d_hist_.p, 0, (size_t)kNumAcContexts * kAcAlphabet * 4, stream_));
   CUDA_OK(cudaMemsetAsync(d_cluster_hist_.p, 0, kMaxClusters * kAcAlphabet * 4, stream_));
@@ -409,8 +404,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   CUDA_OK(cudaEventRecord(ev_[11], stream_));
   // K13 (optional): reconstruction error of the coded frame against the input, for stats.sse / stats.psnr
   if (p.flags & JXLB200_FLAG_QUALITY) {
-    const uint16_t* inv_order[16];
-    for (int o = 0; o < 16; ++o) inv_order[o] = d_inv_order_[o].p;
+    const uint16_t* inv_order[17];
+    for (int o = 0; o < 17; ++o) inv_order[o] = d_inv_order_[o].p;
     if (!d_recon_xyb_.Reserve(3 * plane)) { *err = "device allocation failed"; return false; }
     if (!search) launch_coeff_lists(d_acs_.p, fd, d_coeff_lists_.p, stream_);   // (the search path binned the map already)
     launch_recon_sse(fd, d_q_.p, tables, inv_order, d_cmap_.p, 1.0f / powf(1.25f, (float)(x_qm_scale_ - 2)),
@@ -480,6 +475,29 @@ bool Encoder::Fetch(uint8_t** out, size_t* out_len, std::string* err) {
       cudaStreamSynchronize(stream_) != cudaSuccess) { free(buf); *err = "memcpy"; return false; }
   *out = buf;
   *out_len = codestream_bytes_;
+  return true;
+}
+
+bool Encoder::SetForcedAcs(const uint8_t* acs, int bxs, int bys, std::string* err) {
+  // must be a partition into transforms this path codes, none leaving its 64x64 tile (libjxl's AcStrategyImage invariants)
+  std::vector<uint8_t> seen((size_t)bxs * bys, 0);
+  for (int by = 0; by < bys; ++by) for (int bx = 0; bx < bxs; ++bx) {
+    const uint8_t a = acs[(size_t)by * bxs + bx];
+    if (!(a & 0x80)) continue;
+    const int s = a & 0x7f;
+    const bool ok = s <= 13 || (s >= 18 && s <= 20);
+    if (!ok) { *err = "strategy map: unsupported strategy"; return false; }
+    const int cx = kCoveredX[s], cy = kCoveredY[s];
+    if (bx + cx > bxs || by + cy > bys || (bx & 7) + cx > 8 || (by & 7) + cy > 8) { *err = "strategy map: transform leaves the frame or its tile"; return false; }
+    for (int iy = 0; iy < cy; ++iy) for (int ix = 0; ix < cx; ++ix) {
+      const size_t i = (size_t)(by + iy) * bxs + bx + ix;
+      if ((acs[i] & 0x7f) != s || ((acs[i] & 0x80) != 0) != (ix == 0 && iy == 0) || seen[i]) { *err = "strategy map: inconsistent transform"; return false; }
+      seen[i] = 1;
+    }
+  }
+  for (uint8_t v : seen) if (!v) { *err = "strategy map: uncovered block"; return false; }
+  forced_acs_.assign(acs, acs + (size_t)bxs * bys);
+  forced_bxs_ = bxs; forced_bys_ = bys;
   return true;
 }
 

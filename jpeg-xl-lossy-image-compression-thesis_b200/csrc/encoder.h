@@ -41,6 +41,8 @@ class Encoder {
   bool Fetch(uint8_t** out, size_t* out_len, std::string* err);
   int64_t Dump(int stage, void* dst, size_t cap, std::string* err);
   // parity tap: homogeneity map of caller-supplied XYB planes (see jxlb200_debug_homogeneity)
+  // parity tap: the strategy map the next encodes with JXLB200_FLAG_FORCED_ACS use instead of the search
+  bool SetForcedAcs(const uint8_t* acs, int bxs, int bys, std::string* err);
   bool DebugHomogeneity(const float* x, const float* y, const float* b, int stride, int ysize, float distance, float* out, std::string* err);
   cudaStream_t stream() const { return stream_; }
   // 1 = lowest latency (one group per warp); > 1 packs the rANS chains onto fewer SMs (batch throughput)
@@ -77,11 +79,12 @@ class Encoder {
   DevBuf<float> d_weights_t_[17], d_dequant_t_[17];   // transposed ([hf][vf] of the wide strategy) for kinds 6, 8, 12
   DevBuf<float> d_bias8_;         // k_dct8_v4: Y dequantisation bias per |q|
   DevBuf<uint8_t> d_lastlut8_;    // k_dct8_v4: last scan index per (lane half, mask byte, byte value)
-  DevBuf<uint16_t> d_inv_order_[16];  // per order class: coefficient position -> scan index; [13..15]: classes 4 / 6 / 8 transposed (wide)
+  DevBuf<uint16_t> d_inv_order_[17];  // per order class: coefficient position -> scan index; [13..16]: classes 4 / 6 / 8 / 5 transposed (wide)
   DevBuf<uint8_t> d_cvx_, d_cvy_;
   // per-frame arenas
   DevBuf<uint8_t> d_rgb_;
   uint8_t* h_pinned_ = nullptr; size_t h_pinned_cap_ = 0;
+  std::vector<uint8_t> forced_acs_; int forced_bxs_ = 0, forced_bys_ = 0;
   DevBuf<float> d_xyb_;           // 3 planes
   DevBuf<float> d_mask1x1_, d_pre_, d_qf_, d_mask_, d_homog_, d_acs_entropy_;
   DevBuf<uint8_t> d_acs_;

@@ -18,7 +18,9 @@ namespace jxlb {
 
 // list ids: six 8x8 strategies, then (tall, wide, square) of the three larger levels
 enum { kListDCT = 0, kListID, kList2X2, kList4X4, kList4X8, kList8X4, kList16Tall, kList16Wide, kList16Sq, kList32Tall, kList32Wide,
-       kList32Sq, kList64Tall, kList64Wide, kList64Sq, kNumLists };
+       kList32Sq, kList64Tall, kList64Wide, kList64Sq, kList32Tall4, kList32Wide4, kNumLists };
+
+constexpr int kListHeader = 32;   // counters, then kNumLists lists of nblk entries
 
 __device__ __forceinline__ int list_of_strategy(int s) {
   switch (s) {
@@ -27,11 +29,12 @@ __device__ __forceinline__ int list_of_strategy(int s) {
     case kStratDCT16X8: return kList16Tall; case kStratDCT8X16: return kList16Wide; case kStratDCT16X16: return kList16Sq;
     case kStratDCT32X16: return kList32Tall; case kStratDCT16X32: return kList32Wide; case kStratDCT32X32: return kList32Sq;
     case kStratDCT64X32: return kList64Tall; case kStratDCT32X64: return kList64Wide; case kStratDCT64X64: return kList64Sq;
+    case kStratDCT32X8: return kList32Tall4; case kStratDCT8X32: return kList32Wide4;
     default: return -1;
   }
 }
 
-size_t coeff_list_words(const FrameDim& fd) { return 16 + (size_t)kNumLists * fd.bxs * fd.bys; }
+size_t coeff_list_words(const FrameDim& fd) { return kListHeader + (size_t)kNumLists * fd.bxs * fd.bys; }
 
 __global__ void __launch_bounds__(256) k_coeff_lists(const uint8_t* __restrict__ acs, int nblk, uint32_t* __restrict__ lists) {
   const int i = blockIdx.x * 256 + threadIdx.x, lane = threadIdx.x & 31;
@@ -46,7 +49,7 @@ __global__ void __launch_bounds__(256) k_coeff_lists(const uint8_t* __restrict__
     unsigned base = 0;
     if (lane == leader) base = atomicAdd(&lists[l0], (unsigned)__popc(same));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (li == l0) lists[16 + (size_t)l0 * nblk + base + __popc(same & ((1u << lane) - 1))] = (uint32_t)i;
+    if (li == l0) lists[kListHeader + (size_t)l0 * nblk + base + __popc(same & ((1u << lane) - 1))] = (uint32_t)i;
     todo &= ~same;
   }
 }
@@ -324,15 +327,18 @@ __device__ __noinline__ void coeff8_body(const CoeffArgs& A, unsigned i) {
 // values (top half).  (x, y) below are storage coordinates (long side horizontal): square / tall: y = lane, x = j;
 // wide: x = lane, y = j.
 template <int N, int MODE> struct CoeffGeom {
+  static constexpr bool kWide = MODE == kModeWide2 || MODE == kModeWide4;   // lane = storage column x, value index = storage row y
+  static constexpr int SHORT = MODE == kModeSq ? N : ((MODE == kModeTall2 || MODE == kModeWide2) ? N / 2 : N / 4);   // short side
   static constexpr int H = N / 2;
   static constexpr int W = N;                                   // storage width (long side)
-  static constexpr int HS = MODE == kModeSq ? N : H;            // storage height
-  static constexpr int LANES = MODE == kModeTall2 ? H : N;      // lanes that own coefficients
-  static constexpr int VALS = MODE == kModeWide2 ? H : N;       // values per lane
-  static constexpr int R = MODE == kModeWide2 ? H : N, C = MODE == kModeTall2 ? H : N;   // pixel rows / columns
+  static constexpr int HS = SHORT;                              // storage height
+  static constexpr int LANES = kWide ? N : SHORT;               // lanes that own coefficients
+  static constexpr int VALS = kWide ? SHORT : N;                // values per lane
+  static constexpr int R = kWide ? SHORT : N, C = kWide ? N : SHORT;   // pixel rows / columns
   static constexpr int cxb = C / 8, cyb = R / 8, ncov = cxb * cyb, xs = W / 8, ys = HS / 8;
   static constexpr int S = N == 16 ? (MODE == kModeSq ? kStratDCT16X16 : MODE == kModeTall2 ? kStratDCT16X8 : kStratDCT8X16)
-                         : N == 32 ? (MODE == kModeSq ? kStratDCT32X32 : MODE == kModeTall2 ? kStratDCT32X16 : kStratDCT16X32)
+                         : N == 32 ? (MODE == kModeSq ? kStratDCT32X32 : MODE == kModeTall2 ? kStratDCT32X16 : MODE == kModeWide2 ? kStratDCT16X32
+                                      : MODE == kModeTall4 ? kStratDCT32X8 : kStratDCT8X32)
                                    : (MODE == kModeSq ? kStratDCT64X64 : MODE == kModeTall2 ? kStratDCT64X32 : kStratDCT32X64);
 };
 
@@ -390,7 +396,7 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = j4 + e;
-        const int x = MODE == kModeWide2 ? l : j, y = MODE == kModeWide2 ? j : l;
+        const int x = G::kWide ? l : j, y = G::kWide ? j : l;
         if (x < G::xs && y < G::ys) continue;
         const int hfix = (y >= G::HS / 2 ? 2 : 0) + (x >= G::W / 2 ? 1 : 0);
         const float val = u[j] * (wv[e] * qac * qm_mul);
@@ -399,7 +405,7 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
         r_err += err;
         r_vals += fabsf(v);
         // the half that varies along the lane's own values: x for square / tall lanes, y for wide lanes
-        const bool second = MODE == kModeWide2 ? (y >= G::HS / 2) : (x >= G::W / 2);
+        const bool second = G::kWide ? (y >= G::HS / 2) : (x >= G::W / 2);
         if (c == 1 && v == 0.0f) { if (second) { if (meB < err) meB = err; } else { if (meA < err) meA = err; } }
         if (v != 0.0f) {
           if (second) nzB += fabsf(v); else nzA += fabsf(v);
@@ -412,10 +418,10 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
     }
   }
   // quadrant index hfix = (y half) * 2 + (x half); `first` = the lane sits in the first half of the lane-indexed axis
-  const bool first = MODE == kModeWide2 ? (l < G::W / 2) : (l < G::HS / 2);
+  const bool first = G::kWide ? (l < G::W / 2) : (l < G::HS / 2);
   float s[7];
   s[0] = r_hf; s[1] = r_err; s[2] = r_vals;
-  if constexpr (MODE == kModeWide2) {   // lane = x: first -> quadrants 0 (A: top) and 2 (B: bottom); else 1 and 3
+  if constexpr (G::kWide) {   // lane = x: first -> quadrants 0 (A: top) and 2 (B: bottom); else 1 and 3
     s[3] = first ? nzA : 0.0f; s[4] = first ? 0.0f : nzA; s[5] = first ? nzB : 0.0f; s[6] = first ? 0.0f : nzB;
   } else {                              // lane = y: first -> quadrants 0 (A: left) and 1 (B: right); else 2 and 3
     s[3] = first ? nzA : 0.0f; s[4] = first ? nzB : 0.0f; s[5] = first ? 0.0f : nzA; s[6] = first ? 0.0f : nzB;
@@ -425,7 +431,7 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
   float hfME[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   if (c == 1) {
     float m[4];
-    if constexpr (MODE == kModeWide2) { m[0] = first ? meA : 0.0f; m[1] = first ? 0.0f : meA; m[2] = first ? meB : 0.0f; m[3] = first ? 0.0f : meB; }
+    if constexpr (G::kWide) { m[0] = first ? meA : 0.0f; m[1] = first ? 0.0f : meA; m[2] = first ? meB : 0.0f; m[3] = first ? 0.0f : meB; }
     else { m[0] = first ? meA : 0.0f; m[1] = first ? meB : 0.0f; m[2] = first ? 0.0f : meA; m[3] = first ? 0.0f : meB; }
     lane_maxs<N, G::LANES, 4>(m, xch, l, bar_id);
     hfME[0] = m[0]; hfME[1] = m[1]; hfME[2] = m[2]; hfME[3] = m[3];
@@ -573,7 +579,7 @@ __device__ __noinline__ void coeffsq_body(const CoeffArgs& A, float* smem_f, uns
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = j4 + e;
-            const int x = MODE == kModeWide2 ? l : j, y = MODE == kModeWide2 ? j : l;
+            const int x = G::kWide ? l : j, y = G::kWide ? j : l;
             float in;
             if (c == 1) in = uY[j];
             else in = __fmaf_rn(-factor, uY[j], st[j * N + l]);          // uY holds the dequantised Y by now
@@ -624,7 +630,7 @@ struct CoeffAllArgs {
 __device__ __forceinline__ CoeffArgs list_args(const CoeffAllArgs& AA, int li) {
   CoeffArgs A = AA.base;
   A.w = AA.w[li]; A.dq = AA.dq[li]; A.inv = AA.inv[li];
-  A.count = AA.lists + li; A.list = AA.lists + 16 + (size_t)li * AA.nblk;
+  A.count = AA.lists + li; A.list = AA.lists + kListHeader + (size_t)li * AA.nblk;
   return A;
 }
 
@@ -655,17 +661,22 @@ __global__ void __launch_bounds__(128) k_coeffsq_all(CoeffAllArgs AA) {
   using CG = CoeffSqGeom<N>;
   extern __shared__ __align__(16) float smem_f[];
   constexpr int first = N == 16 ? kList16Tall : (N == 32 ? kList32Tall : kList64Tall);   // tall, wide, square
-  unsigned ctas[3], total = 0;
+  constexpr int nlists = N == 32 ? 5 : 3;                                                  // N = 32: + DCT32X8, DCT8X32
+  unsigned ctas[5], total = 0;
 #pragma unroll
-  for (int m = 0; m < 3; ++m) { ctas[m] = (AA.lists[first + m] + CG::kGroups - 1) / CG::kGroups; total += ctas[m]; }
+  for (int m = 0; m < nlists; ++m) { ctas[m] = (AA.lists[m < 3 ? first + m : kList32Tall4 + m - 3] + CG::kGroups - 1) / CG::kGroups; total += ctas[m]; }
   for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
     unsigned rel = v;
     int m = 0;
     while (rel >= ctas[m]) { rel -= ctas[m]; ++m; }
-    const CoeffArgs A = list_args(AA, first + m);
+    const CoeffArgs A = list_args(AA, m < 3 ? first + m : kList32Tall4 + m - 3);
     if (m == 0) coeffsq_body<N, kModeTall2>(A, smem_f, rel * CG::kGroups);
     else if (m == 1) coeffsq_body<N, kModeWide2>(A, smem_f, rel * CG::kGroups);
-    else coeffsq_body<N, kModeSq>(A, smem_f, rel * CG::kGroups);
+    else if (m == 2) coeffsq_body<N, kModeSq>(A, smem_f, rel * CG::kGroups);
+    else if constexpr (N == 32) {
+      if (m == 3) coeffsq_body<N, kModeTall4>(A, smem_f, rel * CG::kGroups);
+      else coeffsq_body<N, kModeWide4>(A, smem_f, rel * CG::kGroups);
+    }
     __syncthreads();
   }
 }
@@ -673,7 +684,7 @@ __global__ void __launch_bounds__(128) k_coeffsq_all(CoeffAllArgs AA) {
 // ------------------------------------------------------------------------------------------------ host side
 void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s) {
   const size_t nblk = (size_t)fd.bxs * fd.bys;
-  cudaMemsetAsync(lists, 0, 64, s);
+  cudaMemsetAsync(lists, 0, kListHeader * 4, s);
   ++g_kernel_launches;
   k_coeff_lists<<<(unsigned)((nblk + 255) / 256), 256, 0, s>>>(acs, (int)nblk, lists);
 }
@@ -683,7 +694,7 @@ static void launch_coeffsq_all(const CoeffAllArgs& AA, cudaStream_t s) {
   using CG = CoeffSqGeom<N>;
   const size_t smem = CG::kSmemFloats * sizeof(float);
   cudaFuncSetAttribute(k_coeffsq_all<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const size_t max_items = (size_t)AA.nblk / (N * N / 128) + 3;          // the smallest transforms of the class are N x N/2
+  const size_t max_items = (size_t)AA.nblk / (N * N / 256) + 5;          // the smallest transforms of the class are N x N/4
   size_t grid = (max_items + CG::kGroups - 1) / CG::kGroups;
   if (grid > 148 * 8) grid = 148 * 8;
   ++g_kernel_launches;
@@ -715,6 +726,8 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
   AA.w[kList64Tall] = T.w[12]; AA.dq[kList64Tall] = T.dq[12]; AA.inv[kList64Tall] = inv_order[8];
   AA.w[kList64Wide] = T.wT[12]; AA.dq[kList64Wide] = T.dqT[12]; AA.inv[kList64Wide] = inv_order[15];
   AA.w[kList64Sq] = T.w[11]; AA.dq[kList64Sq] = T.dq[11]; AA.inv[kList64Sq] = inv_order[7];
+  AA.w[kList32Tall4] = T.w[7]; AA.dq[kList32Tall4] = T.dq[7]; AA.inv[kList32Tall4] = inv_order[5];
+  AA.w[kList32Wide4] = T.wT[7]; AA.dq[kList32Wide4] = T.dqT[7]; AA.inv[kList32Wide4] = inv_order[16];
   ++g_kernel_launches;
   size_t g8 = (nblk + 63) / 64 + 6;
   if (g8 > 148 * 16) g8 = 148 * 16;

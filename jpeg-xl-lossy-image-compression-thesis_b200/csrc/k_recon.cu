@@ -16,7 +16,8 @@ namespace jxlb {
 namespace {
 
 enum { kListDCT = 0, kListID, kList2X2, kList4X4, kList4X8, kList8X4, kList16Tall, kList16Wide, kList16Sq, kList32Tall, kList32Wide,
-       kList32Sq, kList64Tall, kList64Wide, kList64Sq, kNumLists };
+       kList32Sq, kList64Tall, kList64Wide, kList64Sq, kList32Tall4, kList32Wide4, kNumLists };
+constexpr int kListHeader = 32;
 
 struct ReconArgs {
   FrameDim fd;
@@ -124,10 +125,11 @@ __global__ void __launch_bounds__(64) k_recon8(ReconArgs A) {
 }
 
 template <int N, int MODE> struct ReconGeom {
-  static constexpr int H = N / 2;
-  static constexpr int LANES = MODE == kModeTall2 ? H : N;
-  static constexpr int VALS = MODE == kModeWide2 ? H : N;
-  static constexpr int R = MODE == kModeWide2 ? H : N, C = MODE == kModeTall2 ? H : N;
+  static constexpr bool kWide = MODE == kModeWide2 || MODE == kModeWide4;
+  static constexpr int SHORT = MODE == kModeSq ? N : ((MODE == kModeTall2 || MODE == kModeWide2) ? N / 2 : N / 4);
+  static constexpr int LANES = kWide ? N : SHORT;
+  static constexpr int VALS = kWide ? SHORT : N;
+  static constexpr int R = kWide ? SHORT : N, C = kWide ? N : SHORT;
   static constexpr int cxb = C / 8, cyb = R / 8;
 };
 template <int N> struct ReconSqGeom {
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(256) k_recon_sse(const float* __restrict__ xyb
 template <int S>
 void launch_recon8(ReconArgs A, int list_id, int kind, const uint32_t* lists, const AcsTables& T, size_t nblk, cudaStream_t s) {
   A.dq = T.dq[kind]; A.inv = nullptr;
-  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
+  A.count = lists + list_id; A.list = lists + kListHeader + (size_t)list_id * nblk;
   ++g_kernel_launches;
   k_recon8<S><<<(unsigned)((nblk + 63) / 64), 64, 0, s>>>(A);
 }
@@ -284,7 +286,7 @@ template <int N, int MODE>
 void launch_reconsq(ReconArgs A, int list_id, const float* dq, const uint16_t* inv, const uint32_t* lists, size_t nblk, cudaStream_t s) {
   using RG = ReconSqGeom<N>;
   A.dq = dq; A.inv = inv;
-  A.count = lists + list_id; A.list = lists + 16 + (size_t)list_id * nblk;
+  A.count = lists + list_id; A.list = lists + kListHeader + (size_t)list_id * nblk;
   const size_t smem = (size_t)RG::kGroups * RG::kGroupFloats * sizeof(float);
   cudaFuncSetAttribute(k_reconsq<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const size_t ncov = (size_t)ReconGeom<N, MODE>::cxb * ReconGeom<N, MODE>::cyb;
@@ -320,6 +322,8 @@ void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T
   launch_reconsq<64, kModeTall2>(A, kList64Tall, T.dq[12], inv_order[8], lists, nblk, s);
   launch_reconsq<64, kModeWide2>(A, kList64Wide, T.dqT[12], inv_order[15], lists, nblk, s);
   launch_reconsq<64, kModeSq>(A, kList64Sq, T.dq[11], inv_order[7], lists, nblk, s);
+  launch_reconsq<32, kModeTall4>(A, kList32Tall4, T.dq[7], inv_order[5], lists, nblk, s);
+  launch_reconsq<32, kModeWide4>(A, kList32Wide4, T.dqT[7], inv_order[16], lists, nblk, s);
   ++g_kernel_launches;
   k_recon_sse<<<dim3((fd.xsize + 255) / 256, fd.ysize), 256, 0, s>>>(scratch_xyb, fd, rgb, stride, tables, sse3);
 }

@@ -400,7 +400,9 @@ template <int S> __device__ __forceinline__ void inv8x8(float* c, float* p) {
 // N x N squares, N lanes.  MODE: one square transform, two tall halves (left | right, N rows x N/2 columns
 // each) or two wide halves (top / bottom, N/2 rows x N columns each).
 // ====================================================================================================
-enum { kModeSq = 0, kModeTall2 = 1, kModeWide2 = 2 };
+// kModeTall4 / kModeWide4: ONE N x N/4 (resp. N/4 x N) transform in the first quarter of the square (DCT32X8 / DCT8X32,
+// which no search proposes: they are only reached through a caller-supplied strategy map); the rest of the square is zero
+enum { kModeSq = 0, kModeTall2 = 1, kModeWide2 = 2, kModeTall4 = 3, kModeWide4 = 4 };
 
 // XOR swizzle of the 16-byte chunks of a row: quarter-warps of row accesses and whole-warp column accesses hit
 // 32 distinct banks (N = 16: two rows share a 128-byte line, so the row index is halved first)
@@ -452,22 +454,26 @@ template <int N> struct SquareXform {
   template <int MODE>
   static __device__ __forceinline__ void forward(float* t, int l, const Col& c, float* v, float* u, int bar_id) {
     if constexpr (MODE == kModeTall2) { dct1d<N / 2>(v); dct1d<N / 2>(v + N / 2); }
+    else if constexpr (MODE == kModeTall4) dct1d<N / 4>(v);
     else dct1d<N>(v);
     store_row(t, l, v);
     sync(bar_id);
     load_col(t, c, u);
     if constexpr (MODE == kModeWide2) { dct1d<N / 2>(u); dct1d<N / 2>(u + N / 2); }
+    else if constexpr (MODE == kModeWide4) dct1d<N / 4>(u);
     else dct1d<N>(u);
   }
   // inverse: u = lane's coefficient column in (destroyed), v = lane's pixel row out
   template <int MODE>
   static __device__ __forceinline__ void inverse(float* t, int l, const Col& c, float* u, float* v, int bar_id) {
     if constexpr (MODE == kModeWide2) { idct1d<N / 2>(u); idct1d<N / 2>(u + N / 2); }
+    else if constexpr (MODE == kModeWide4) idct1d<N / 4>(u);
     else idct1d<N>(u);
     store_col(t, c, u);
     sync(bar_id);
     load_row(t, l, v);
     if constexpr (MODE == kModeTall2) { idct1d<N / 2>(v); idct1d<N / 2>(v + N / 2); }
+    else if constexpr (MODE == kModeTall4) idct1d<N / 4>(v);
     else idct1d<N>(v);
   }
 };

@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY, PROPOSAL_COMBINED = 0, 1, 2, 3
-FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY = 1, 2, 4
+FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, FLAG_FORCED_ACS = 1, 2, 4, 8
 
 # stage id -> (name, numpy dtype)   (JXLB200_STAGE_* in include/jxlb200.h)
 STAGES = {
@@ -130,6 +130,8 @@ def load_library() -> ctypes.CDLL:
     lib.jxlb200_dump.restype = ctypes.c_int64
     lib.jxlb200_dump.argtypes = [vp, ctypes.c_int, vp, ctypes.c_size_t]
     lib.jxlb200_dims.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32)]
+    lib.jxlb200_debug_set_strategy_map.restype = ctypes.c_int
+    lib.jxlb200_debug_set_strategy_map.argtypes = [vp, vp, ctypes.c_uint32, ctypes.c_uint32]
     lib.jxlb200_debug_homogeneity.restype = ctypes.c_int
     lib.jxlb200_debug_homogeneity.argtypes = [vp, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, vp]
     _LIB = lib
@@ -268,6 +270,13 @@ class Encoder:
         self._lib.jxlb200_free(out)
         return data
 
+    def set_strategy_map(self, acs) -> None:
+        """AC-strategy map (bys x bxs uint8, raw strategy | 0x80 on first blocks) that encodes with FLAG_FORCED_ACS use
+        instead of the search: jxlb200_debug_set_strategy_map."""
+        acs = np.ascontiguousarray(acs, dtype=np.uint8)
+        if self._lib.jxlb200_debug_set_strategy_map(self._ctx, acs.ctypes.data, acs.shape[1], acs.shape[0]) != 0:
+            raise EncodeError(self._err())
+
     def homogeneity_map(self, x, y, b, distance: float) -> np.ndarray:
         """r_h, r_v, r_d of every 8x8 block of caller-supplied XYB planes (rows x stride float32 arrays; the stride is the
         reference's `src_stride` bound, the row count its `src_ysize`): jxlb200_debug_homogeneity."""
@@ -277,7 +286,7 @@ class Encoder:
         rc = self._lib.jxlb200_debug_homogeneity(self._ctx, x.ctypes.data, y.ctypes.data, b.ctypes.data, stride, rows,
                                                  float(distance), out.ctypes.data)
         if rc != 0:
-            raise EncodeError(self.last_error())
+            raise EncodeError(self._err())
         return out
 
     def dump(self, stage) -> np.ndarray:

@@ -21,6 +21,14 @@ void* jxo_encode(const uint8_t* rgb, int w, int h, size_t stride, const JxoParam
   EncodeFrame(rgb, w, h, stride, pp, f);
   return f;
 }
+// encode with a caller-supplied strategy map (bys * bxs bytes, raw strategy | 0x80 on first blocks) instead of the search
+void* jxo_encode_forced(const uint8_t* rgb, int w, int h, size_t stride, const JxoParams* p, const uint8_t* acs, size_t n) {
+  Frame* f = new Frame();
+  Params pp; pp.distance = p->distance; pp.effort = p->effort; pp.proposal = p->proposal; pp.flags = p->flags | kFlagForcedAcs;
+  f->forced_acs.assign(acs, acs + n);
+  EncodeFrame(rgb, w, h, stride, pp, f);
+  return f;
+}
 // self-decoder: parses a codestream back into the integer stages (dc_quant, acs, raw_qf, coeffs, ...)
 void* jxo_decode(const uint8_t* data, size_t size) {
   Frame* f = new Frame();

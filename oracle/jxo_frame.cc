@@ -128,7 +128,12 @@ bool EncodeFrame(const uint8_t* rgb, int w, int h, size_t stride, const Params& 
   f->cmap.assign((size_t)2 * fd.txs * fd.tys, 0);
   f->acs.assign(nblk, 0x80 | DCT);
   f->acs_entropy.assign(nblk, 0.0f);
-  if (!(p.flags & kFlagFixedDct8)) AcStrategySearch(f);
+  if (p.flags & kFlagForcedAcs) {
+    if (f->forced_acs.size() != nblk) { f->error = "forced strategy map of the wrong size"; return false; }
+    f->acs = f->forced_acs;
+  } else if (!(p.flags & kFlagFixedDct8)) {
+    AcStrategySearch(f);
+  }
   AdjustQuantField(f);
   f->raw_qf.assign(nblk, 0);
   SetRawQuantField(f->qf_float.data(), nblk, f->q, f->raw_qf.data());

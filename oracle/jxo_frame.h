@@ -12,7 +12,7 @@ struct Params {
   uint32_t proposal = 0;  // 0 none, 1 partitioning, 2 factored-entropy, 3 combined
   uint32_t flags = 0;     // bit0: fixed DCT8 strategy; bit1: uniform quant field
 };
-enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u };
+enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u, kFlagForcedAcs = 8u };
 
 // stage ids — identical to JXLB200_STAGE_* in include/jxlb200.h
 enum Stage : int {
@@ -34,6 +34,7 @@ struct Frame {
   std::vector<float> mask;            // bys * bxs
   std::vector<float> mask1x1;         // ys_pad * pitch
   std::vector<float> homog;           // blocks * 3 (r_h, r_v, r_d)
+  std::vector<uint8_t> forced_acs;    // kFlagForcedAcs: the strategy map to code with instead of searching (parity tap)
   std::vector<uint8_t> acs;           // bys * bxs : raw strategy | 0x80 if first block
   std::vector<float> acs_entropy;     // bys * bxs : entropy estimate left by the search
   std::vector<int32_t> raw_qf;        // bys * bxs

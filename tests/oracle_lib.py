@@ -36,6 +36,8 @@ class Oracle:
         vp = ctypes.c_void_p
         lib.jxo_encode.restype = vp
         lib.jxo_encode.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(Params)]
+        lib.jxo_encode_forced.restype = vp
+        lib.jxo_encode_forced.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(Params), vp, ctypes.c_size_t]
         lib.jxo_decode.restype = vp
         lib.jxo_decode.argtypes = [vp, ctypes.c_size_t]
         lib.jxo_reconstruct.restype = ctypes.c_int
@@ -73,6 +75,15 @@ class Oracle:
         image = np.ascontiguousarray(image)
         p = Params(distance, effort, proposal, flags)
         h = self.lib.jxo_encode(image.ctypes.data, image.shape[1], image.shape[0], image.strides[0], ctypes.byref(p))
+        return Frame(self, h)
+
+    def encode_forced(self, image, acs, distance=1.0, effort=7, proposal=0, flags=0):
+        """encode with the given AC-strategy map (uint8, raw strategy | 0x80 on first blocks) instead of the search"""
+        image = np.ascontiguousarray(image)
+        acs = np.ascontiguousarray(acs, dtype=np.uint8)
+        p = Params(distance, effort, proposal, flags)
+        h = self.lib.jxo_encode_forced(image.ctypes.data, image.shape[1], image.shape[0], image.strides[0], ctypes.byref(p),
+                                       acs.ctypes.data, acs.size)
         return Frame(self, h)
 
     def decode(self, codestream):

@@ -103,3 +103,29 @@ def test_group_stream_taps(pkg, oracle, encoder):
         ora = oracle.encode(img, 1.0, 7, 3, flags)
         assert np.array_equal(encoder.dump("group_offsets"), ora.dump("group_offsets"))
         assert np.array_equal(encoder.dump("group_streams"), ora.dump("group_streams"))
+
+
+def test_forced_strategy_map_parity(pkg, oracle, encoder):
+    """Row U5 through the C ABI: a caller-supplied strategy map (jxlb200_debug_set_strategy_map + JXLB200_FLAG_FORCED_ACS) that
+    uses every transform of the subset, DCT32X8 / DCT8X32 included: coefficients, statistics, codestream and the quality
+    statistics equal the oracle's."""
+    from test_oracle_entropy import every_strategy_map
+    from test_gpu_parity import _valid_coeffs
+    for (w, h, seed, dist) in ((264, 200, 5, 1.0), (520, 260, 9, 0.5), (100, 60, 2, 3.0)):
+        img = pkg.synth_image(w, h, 70 + seed)
+        d = pkg.frame_dims(w, h)
+        acs = every_strategy_map(d["bys"], d["bxs"], seed=seed)
+        encoder.set_strategy_map(acs)
+        data, st = encoder.encode(img, dist, 7, 0, pkg.FLAG_FORCED_ACS | pkg.FLAG_QUALITY)
+        ora = oracle.encode_forced(img, acs, dist, 7, 0, 0)
+        assert ora.error == ""
+        for stage in ("acs", "raw_qf", "dc_quant", "nzeros"):
+            assert np.array_equal(encoder.dump(stage), ora.dump(stage)), stage
+        assert np.array_equal(_valid_coeffs(encoder.dump("coeffs"), d), _valid_coeffs(ora.dump("coeffs"), d))
+        assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream"))
+        assert st.sse == [int(v) for v in ora.sse(img)]
+    with pytest.raises(pkg.EncodeError):
+        bad = acs.copy(); bad[0, 0] = 5 | 0x80          # a 32x32 transform declared on a map that does not cover it
+        encoder.set_strategy_map(bad)
+    with pytest.raises(pkg.EncodeError):
+        encoder.encode(pkg.synth_image(64, 64, 1), 1.0, 7, 0, pkg.FLAG_FORCED_ACS)   # map of another frame size

@@ -232,3 +232,59 @@ def test_sse_tap_matches_reconstruction(pkg, oracle):
         d = rec.astype(np.int64) - img.astype(np.int64)
         assert [int(v) for v in sse] == [int((d[:, :, c] ** 2).sum()) for c in range(3)]
         f.close()
+
+
+COVERED.update({8: (1, 4), 9: (4, 1)})   # DCT32X8, DCT8X32: reachable through a supplied map only
+
+
+def every_strategy_map(bys, bxs, seed=0):
+    """A valid partition that uses every transform of the subset, including DCT32X8 / DCT8X32 (which libjxl's merge table
+    never proposes): per 64x64 tile a seeded random greedy fill, largest shapes first."""
+    rng = np.random.default_rng(seed)
+    acs = np.zeros((bys, bxs), dtype=np.uint8)
+    shapes = [s for s in COVERED if COVERED[s] != (1, 1)]
+    singles = [s for s in COVERED if COVERED[s] == (1, 1)]
+    tile = 0
+    for ty in range(0, bys, 8):
+        for tx in range(0, bxs, 8):
+            th, tw = min(8, bys - ty), min(8, bxs - tx)
+            used = np.zeros((th, tw), dtype=bool)
+            for y in range(th):
+                for x in range(tw):
+                    if used[y, x]:
+                        continue
+                    cand = [s for s in shapes if x + COVERED[s][0] <= tw and y + COVERED[s][1] <= th and
+                            not used[y:y + COVERED[s][1], x:x + COVERED[s][0]].any()]
+                    first = shapes[tile % len(shapes)]             # every multi-block shape opens some tile
+                    if x == 0 and y == 0 and first in cand:
+                        s = first
+                    else:
+                        s = int(rng.choice(cand)) if cand and rng.random() < 0.7 else int(rng.choice(singles))
+                    cx, cy = COVERED[s]
+                    used[y:y + cy, x:x + cx] = True
+                    acs[ty + y:ty + y + cy, tx + x:tx + x + cx] = s
+                    acs[ty + y, tx + x] |= 0x80
+            tile += 1
+    return acs
+
+
+
+def test_forced_strategy_map_codes_every_transform(pkg, oracle):
+    """Row U5: with a caller-supplied strategy map every transform of the subset — DCT32X8 / DCT8X32 included — is coded,
+    the codestream decodes to exactly what was coded, and the decoded pixels are the input at the distance's quality."""
+    img = pkg.synth_image(264, 200, 77)
+    d = oracle.dims(264, 200)
+    acs = every_strategy_map(d["bys"], d["bxs"], seed=5)
+    check_partition(acs.reshape(-1), d["bys"], d["bxs"])
+    f = oracle.encode_forced(img, acs, 1.0, 7, 0, 0)
+    assert f.error == "", f.error
+    assert np.array_equal(f.dump("acs").reshape(d["bys"], d["bxs"]), acs)
+    used = set(np.unique(acs[acs >= 128] & 0x7F).tolist())
+    assert {8, 9, 18, 19, 20, 1, 2} <= used
+    cs = f.dump("codestream").tobytes()
+    dec = oracle.decode(cs)
+    assert dec.error == "", dec.error
+    for st in LOSSLESS_STAGES:
+        assert np.array_equal(f.dump(st), dec.dump(st)), st
+    rec = oracle.decode_pixels(cs, 264, 200)
+    assert rec is not None and _psnr(img, rec) > 34.0

@@ -60,6 +60,33 @@ bool Encoder::Init(int device, std::string* err) {
     }
   }
   {
+    // the tables k_acs_evalsq<32 / 64> reads from global memory, in 16-byte chunks: [c][chunk][lane row][4] — the lanes of
+    // a warp then fetch one contiguous run per load instead of one cache line each
+    struct Src { int slot, kind; bool transposed; size_t chan, row; };
+    const Src srcs[6] = {{0, 8, false, 512, 32}, {1, 8, true, 512, 16}, {2, 5, false, 1024, 32},
+                         {3, 12, false, 2048, 64}, {4, 12, true, 2048, 32}, {5, 11, false, 4096, 64}};
+    for (const Src& sc : srcs) {
+      std::vector<float> w;
+      host_quant_weights(sc.kind, &w);
+      if (sc.transposed) {
+        const size_t W = sc.kind == 12 ? 64 : 32, H = W / 2;
+        std::vector<float> wt(w.size());
+        for (size_t c = 0; c < 3; ++c) for (size_t y = 0; y < H; ++y) for (size_t x = 0; x < W; ++x) wt[c * W * H + x * H + y] = w[c * W * H + y * W + x];
+        w.swap(wt);
+      }
+      const size_t rows = sc.chan / sc.row;
+      std::vector<float> wc(w.size()), dc(w.size());
+      for (size_t c = 0; c < 3; ++c) for (size_t r = 0; r < rows; ++r) for (size_t j = 0; j < sc.row; ++j) {
+        const float v = w[c * sc.chan + r * sc.row + j];
+        const size_t o = c * sc.chan + (j / 4) * rows * 4 + r * 4 + (j % 4);
+        wc[o] = v; dc[o] = 1.0f / v;
+      }
+      if (!d_weights_c_[sc.slot].Reserve(wc.size()) || !d_dequant_c_[sc.slot].Reserve(dc.size())) { *err = "alloc"; return false; }
+      CUDA_OK(cudaMemcpy(d_weights_c_[sc.slot].p, wc.data(), wc.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(d_dequant_c_[sc.slot].p, dc.data(), dc.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  {
     if (const char* e = getenv("JXLB200_DCT8_ROWS")) dct8_rows_ = atoi(e);
     if (const char* e = getenv("JXLB200_DCT8_TPS")) dct8_tps_ = atoi(e);
   }
@@ -149,6 +176,7 @@ void Encoder::Destroy() {
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); d_weights_t_[k].Release(); d_dequant_t_[k].Release(); }
   for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
+  for (int k = 0; k < 6; ++k) { d_weights_c_[k].Release(); d_dequant_c_[k].Release(); }
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 17; ++o) d_inv_order_[o].Release();
@@ -322,6 +350,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
     tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; tables.wT[k] = d_weights_t_[k].p; tables.dqT[k] = d_dequant_t_[k].p;
   }
   for (int k = 0; k < 4; ++k) { tables.w8[k] = d_w8_[k].p; tables.dq8[k] = d_dq8_[k].p; }
+  for (int k = 0; k < 6; ++k) { tables.wC[k] = d_weights_c_[k].p; tables.dqC[k] = d_dequant_c_[k].p; }
   if (forced) {
     CUDA_OK(cudaMemcpyAsync(d_acs_.p, forced_acs_.data(), nblk, cudaMemcpyHostToDevice, stream_));
     CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));

@@ -35,7 +35,12 @@ struct AcsParams {
 // quantisation weights / their inverses per table kind; wT / dqT: the same tables transposed ([hf][vf] of the WIDE
 // strategy of kinds 6, 8, 12: the order a lane that owns one horizontal frequency reads them in)
 // w8 / dq8: the 8x8 tables of DCT, DCT4X4, DCT4X8, DCT8X4 in the lane order of k_acs_evalsq<8> ([lane][j])
-struct AcsTables { const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; const float* w8[4]; const float* dq8[4]; };
+// wC / dqC: the tables of k_acs_evalsq<32> (slots 0..2 = tall halves, wide halves, square) and <64> (3..5) in 16-byte
+// chunks, [c][chunk][lane row][4]
+struct AcsTables {
+  const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; const float* w8[4]; const float* dq8[4];
+  const float* wC[6]; const float* dqC[6];
+};
 size_t acs_work_floats(const FrameDim& fd);   // candidate-value tables of the search
 size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-aligned squares (uint32 words)
 void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,

@@ -28,6 +28,8 @@ struct jxlb200_ctx {
   int ans_warps_single = 8;           // warps per rANS CTA for a single image (4: 2.51 ms, 8: 2.45 ms, 16: 2.65 ms per 4K frame) ($JXLB200_ANS_WARPS_SINGLE)
   int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
   int ans_gpw = 2;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
+  std::vector<uint8_t> forced_acs;    // jxlb200_debug_set_strategy_map: handed to every pipeline
+  int forced_bxs = 0, forced_bys = 0;
   std::string err;
   Encoder* pipe(int i) { return i == 0 ? &enc : extra[i - 1]; }
 };
@@ -37,6 +39,7 @@ static bool ensure_pipelines(jxlb200_ctx* ctx, int n) {
     Encoder* e = new Encoder();
     std::string err;
     if (!e->Init(ctx->device, &err)) { delete e; ctx->err = err; return false; }
+    if (!ctx->forced_acs.empty() && !e->SetForcedAcs(ctx->forced_acs.data(), ctx->forced_bxs, ctx->forced_bys, &err)) { delete e; ctx->err = err; return false; }
     ctx->extra.push_back(e);
   }
   return true;
@@ -259,7 +262,10 @@ int jxlb200_debug_set_strategy_map(jxlb200_ctx* ctx, const uint8_t* acs, uint32_
   if (!ctx) return -1;
   if (!acs || bxs == 0 || bys == 0 || (uint64_t)bxs * bys > (1ull << 22)) return fail(ctx, "invalid strategy map");
   std::string e;
-  if (!ctx->enc.SetForcedAcs(acs, (int)bxs, (int)bys, &e)) return fail(ctx, e);
+  ctx->forced_acs.assign(acs, acs + (size_t)bxs * bys);
+  ctx->forced_bxs = (int)bxs; ctx->forced_bys = (int)bys;
+  for (int p = 0; p <= (int)ctx->extra.size(); ++p)
+    if (!ctx->pipe(p)->SetForcedAcs(acs, (int)bxs, (int)bys, &e)) return fail(ctx, e);
   return 0;
 }
 

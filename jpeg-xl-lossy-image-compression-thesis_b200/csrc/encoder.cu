@@ -159,6 +159,39 @@ bool Encoder::Init(int device, std::string* err) {
       }
     }
   }
+  {
+    // coefficient-stage tables of the 16 / 32 / 64-sized strategies (list order of k_coeff.cu: tall, wide, square per level,
+    // then DCT32X8, DCT8X32): lane order, 16-byte chunks: [c][chunk][lane][4].  Tall and square strategies keep the stored
+    // orientation (lane = storage row); wide ones are transposed (lane = storage column).
+    struct Src { int kind, order_class; bool wide; size_t lanes, vals; };
+    const Src srcs[11] = {{6, 4, false, 8, 16},  {6, 4, true, 16, 8},   {4, 2, false, 16, 16}, {8, 6, false, 16, 32},
+                          {8, 6, true, 32, 16},  {5, 3, false, 32, 32}, {12, 8, false, 32, 64}, {12, 8, true, 64, 32},
+                          {11, 7, false, 64, 64}, {7, 5, false, 8, 32},  {7, 5, true, 32, 8}};
+    static const int rep[13] = {0, 3, 4, 5, 6, 8, 10, 18, 19, -1, -1, -1, -1};
+    for (int i = 0; i < 11; ++i) {
+      const Src& sc = srcs[i];
+      std::vector<float> w;
+      host_quant_weights(sc.kind, &w);
+      std::vector<uint16_t> order;
+      host_natural_order(rep[sc.order_class], &order);
+      std::vector<uint16_t> inv(order.size());
+      for (size_t k = 0; k < order.size(); ++k) inv[order[k]] = (uint16_t)k;
+      const size_t L = sc.lanes, V = sc.vals, n = L * V;
+      std::vector<float> wj(3 * n), dj(3 * n);
+      std::vector<uint16_t> ij(n);
+      for (size_t l = 0; l < L; ++l) for (size_t j = 0; j < V; ++j) {
+        // stored position: tall / square [lane][j]; wide: the stored table is [j][lane] (V rows of L)
+        const size_t pos = sc.wide ? j * L + l : l * V + j;
+        const size_t o = (j / 4) * L * 4 + l * 4 + (j % 4);
+        for (size_t c = 0; c < 3; ++c) { wj[c * n + o] = w[c * n + pos]; dj[c * n + o] = 1.0f / w[c * n + pos]; }
+        ij[o] = inv[pos];
+      }
+      if (!d_weights_j_[i].Reserve(wj.size()) || !d_dequant_j_[i].Reserve(dj.size()) || !d_inv_j_[i].Reserve(ij.size())) { *err = "alloc"; return false; }
+      CUDA_OK(cudaMemcpy(d_weights_j_[i].p, wj.data(), wj.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(d_dequant_j_[i].p, dj.data(), dj.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(d_inv_j_[i].p, ij.data(), ij.size() * 2, cudaMemcpyHostToDevice));
+    }
+  }
   if (!d_cvx_.Reserve(27) || !d_cvy_.Reserve(27) || !d_q_.Reserve(1)) { *err = "alloc"; return false; }
   CUDA_OK(cudaMemcpy(d_cvx_.p, kCoveredX, 27, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(d_cvy_.p, kCoveredY, 27, cudaMemcpyHostToDevice));
@@ -177,6 +210,7 @@ void Encoder::Destroy() {
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); d_weights_t_[k].Release(); d_dequant_t_[k].Release(); }
   for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
   for (int k = 0; k < 6; ++k) { d_weights_c_[k].Release(); d_dequant_c_[k].Release(); }
+  for (int k = 0; k < 11; ++k) { d_weights_j_[k].Release(); d_dequant_j_[k].Release(); d_inv_j_[k].Release(); }
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 17; ++o) d_inv_order_[o].Release();
@@ -351,6 +385,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   }
   for (int k = 0; k < 4; ++k) { tables.w8[k] = d_w8_[k].p; tables.dq8[k] = d_dq8_[k].p; }
   for (int k = 0; k < 6; ++k) { tables.wC[k] = d_weights_c_[k].p; tables.dqC[k] = d_dequant_c_[k].p; }
+  for (int k = 0; k < 11; ++k) { tables.wJ[k] = d_weights_j_[k].p; tables.dqJ[k] = d_dequant_j_[k].p; tables.invJ[k] = d_inv_j_[k].p; }
   if (forced) {
     CUDA_OK(cudaMemcpyAsync(d_acs_.p, forced_acs_.data(), nblk, cudaMemcpyHostToDevice, stream_));
     CUDA_OK(cudaMemsetAsync(d_acs_entropy_.p, 0, nblk * 4, stream_));

@@ -75,6 +75,8 @@ class Encoder {
   DevBuf<float> d_lut_, d_recon_tab_;
   DevBuf<float> d_weights_[17];
   DevBuf<float> d_dequant_[17];
+  DevBuf<float> d_weights_j_[11], d_dequant_j_[11];  // coefficient-stage tables in 16-byte chunks (AcsTables::wJ)
+  DevBuf<uint16_t> d_inv_j_[11];
   DevBuf<float> d_weights_c_[6], d_dequant_c_[6];   // 32 / 64-sized search tables in 16-byte chunks (AcsTables::wC)
   DevBuf<float> d_w8_[4], d_dq8_[4];   // 8x8 tables of DCT, DCT4X4, DCT4X8, DCT8X4 in the lane order of the search kernel
   DevBuf<float> d_weights_t_[17], d_dequant_t_[17];   // transposed ([hf][vf] of the wide strategy) for kinds 6, 8, 12

@@ -376,9 +376,31 @@ __device__ __forceinline__ void lane_maxs(float (&v)[K], float* xch, int l, int 
   }
 }
 
-// oracle AdjustQuantBlockAC for a lane group; u = the lane's coefficients, wrow = its row of the lane-ordered table
+// Shared memory of one lane group: three N x (N + 4) tiles (one per channel), the lowest-frequency scratch of the DC
+// extraction, and (N = 64) the exchange rows of the two-warp sums.  A channel's tile is first the landing zone of its
+// pixels (coalesced 16-byte cp.async: one instruction = four whole rows), then the transposition buffer of the transform,
+// then the lane-ordered home of the coefficients: lane hf keeps its N values in row hf.  The pitch is 4 floats past a
+// multiple of 32: 16-byte accesses to a lane's own row and 4-byte accesses down a column are both conflict-free (N = 16:
+// the two groups of a warp are 16 banks apart).
+// Everything after the transform runs as rolled loops over 16-byte chunks of the lane's row (tables are stored in the same
+// chunks, [c][chunk][lane][4], so a warp's table load is one contiguous run): the code of a transform is a few thousand
+// instructions that stay in the instruction cache, where the fully unrolled version streamed 35 000 of them once per item
+// and spent 40 % of its time waiting for instruction fetches (ncu, profiles/r02k).
+template <int N> struct CoeffSqGeom {
+  static constexpr int kGroupsPerWarp = N == 16 ? 2 : 1;
+  static constexpr int kThreads = N == 64 ? 64 : 128;
+  static constexpr int kGroups = N == 64 ? 1 : 4 * kGroupsPerWarp;          // transforms per CTA pass
+  static constexpr int kPitch = N + 4;
+  static constexpr int kSq = N * kPitch;
+  static constexpr int kLlf = N == 16 ? 16 : 3 * (N / 8) * (N / 8);          // [c][cyb][cxb]
+  static constexpr int kXch = N == 64 ? 7 * 64 : 0;
+  static constexpr int kGroupFloats = 3 * kSq + kLlf + kXch;                 // (N = 16: 976 = 16 mod 32)
+  static constexpr int kSmemFloats = kGroups * kGroupFloats;
+};
+
+// oracle AdjustQuantBlockAC for a lane group; row = the lane's coefficients, wl = the lane's slot of the chunked table
 template <int N, int MODE>
-__device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __restrict__ wrow, int c, float scale, float qm_mul, int quant,
+__device__ __forceinline__ int adjust_quant_sq(const float* row, const float* __restrict__ wl, int c, float scale, float qm_mul, int quant,
                                                float thr[4], int l, bool owner, float* xch, int bar_id) {
   using G = CoeffGeom<N, MODE>;
   const float qac = scale * (float)quant;
@@ -388,24 +410,30 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
     if (thr[i] < 0.54f) thr[i] = 0.54f;
   }
   float r_hf = 0.0f, r_err = 0.0f, r_vals = 0.0f, nzA = 0.0f, nzB = 0.0f, meA = 0.0f, meB = 0.0f;
+  // quadrant index hfix = (y half) * 2 + (x half); `first` = the lane sits in the first half of the lane-indexed axis;
+  // A / B = first / second half of the axis the lane's own values run along
+  const bool first = G::kWide ? (l < G::W / 2) : (l < G::HS / 2);
+  const float thrA = G::kWide ? (first ? thr[0] : thr[1]) : (first ? thr[0] : thr[2]);
+  const float thrB = G::kWide ? (first ? thr[2] : thr[3]) : (first ? thr[1] : thr[3]);
   if (owner) {
-#pragma unroll
+    const float wmul = qac;   // (w * qac) * qm_mul, in this order
+#pragma unroll 1
     for (int j4 = 0; j4 < G::VALS; j4 += 4) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j4));
-      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wl + (size_t)(j4 >> 2) * G::LANES * 4));
+      const float4 u4 = *reinterpret_cast<const float4*>(row + j4);
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, uv[4] = {u4.x, u4.y, u4.z, u4.w};
+      const bool second = j4 >= G::VALS / 2;
+      const float t = second ? thrB : thrA;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = j4 + e;
         const int x = G::kWide ? l : j, y = G::kWide ? j : l;
         if (x < G::xs && y < G::ys) continue;
-        const int hfix = (y >= G::HS / 2 ? 2 : 0) + (x >= G::W / 2 ? 1 : 0);
-        const float val = u[j] * (wv[e] * qac * qm_mul);
-        const float v = (fabsf(val) < thr[hfix]) ? 0.0f : rintf(val);
+        const float val = uv[e] * (wv[e] * wmul * qm_mul);
+        const float v = (fabsf(val) < t) ? 0.0f : rintf(val);
         const float err = fabsf(val - v);
         r_err += err;
         r_vals += fabsf(v);
-        // the half that varies along the lane's own values: x for square / tall lanes, y for wide lanes
-        const bool second = G::kWide ? (y >= G::HS / 2) : (x >= G::W / 2);
         if (c == 1 && v == 0.0f) { if (second) { if (meB < err) meB = err; } else { if (meA < err) meA = err; } }
         if (v != 0.0f) {
           if (second) nzB += fabsf(v); else nzA += fabsf(v);
@@ -417,8 +445,6 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
       }
     }
   }
-  // quadrant index hfix = (y half) * 2 + (x half); `first` = the lane sits in the first half of the lane-indexed axis
-  const bool first = G::kWide ? (l < G::W / 2) : (l < G::HS / 2);
   float s[7];
   s[0] = r_hf; s[1] = r_err; s[2] = r_vals;
   if constexpr (G::kWide) {   // lane = x: first -> quadrants 0 (A: top) and 2 (B: bottom); else 1 and 3
@@ -439,181 +465,212 @@ __device__ __forceinline__ int adjust_quant_sq(const float* u, const float* __re
   return adjust_close<G::S>(c, quant, G::ncov, s[0], s[1], s[2], hfNZ, hfME, thr);
 }
 
-template <int N> struct CoeffSqGeom {
-  static constexpr int kGroupsPerWarp = N == 16 ? 2 : 1;
-  static constexpr int kThreads = 128;
-  static constexpr int kGroups = N == 64 ? 2 : 4 * kGroupsPerWarp;           // transforms per CTA pass
-  static constexpr int kSq = N == 16 ? 256 + 16 : N * N;                    // one square buffer (16: skewed)
-  static constexpr int kGroupFloats = 3 * kSq + 3 * 64 + 7 * 64;            // transposition square, X / B stash, LLF, exchange
-  static constexpr int kSmemFloats = kGroups * kGroupFloats;
-};
-
 template <int N, int MODE>
 __device__ __noinline__ void coeffsq_body(const CoeffArgs& A, float* smem_f, unsigned item0) {
   using G = CoeffGeom<N, MODE>;
   using CG = CoeffSqGeom<N>;
   using SX = SquareXform<N>;
+  constexpr int P = CG::kPitch;
   const FrameDim& fd = A.fd;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int l = N == 64 ? (tid & 63) : (lane & (N - 1));
-  const int grp = N == 64 ? (tid >> 6) : warp * CG::kGroupsPerWarp + (N == 16 ? (lane >> 4) : 0);
+  const int l = N == 64 ? tid : (lane & (N - 1));
+  const int grp = N == 64 ? 0 : warp * CG::kGroupsPerWarp + (N == 16 ? (lane >> 4) : 0);
   float* base = smem_f + grp * CG::kGroupFloats;
-  float* tbuf = base; float* stash[2] = {base + CG::kSq, base + 2 * CG::kSq};
-  float* llf = base + 3 * CG::kSq;          // [c][64]
-  float* xch = llf + 3 * 64;                // [7][64]
-  const typename SX::Col col = SX::col_of(l);
+  float* llf = base + 3 * CG::kSq;          // [c][cyb][cxb]: lowest frequencies, then the DC values
+  float* xch = llf + CG::kLlf;              // [7][64] (N = 64)
   const unsigned n = *A.count;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
   const bool owner = l < G::LANES;
-  const int bar_id = 1 + grp;   // (N = 64: each pair of warps meets at its own named barrier)
+  const int bar_id = 1;
+  const unsigned item = item0 + grp;
+  const bool active = item < n;
+  const size_t bi = active ? A.list[item] : 0;
+  const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
+  const int orig = active ? A.raw_qf[bi] : 1;
+  // ---- all three channels' pixels start their way to shared memory (only the transform's own R x C pixels; the rest of
+  // each tile is zero-filled)
+  SX::sync(bar_id);                          // (the previous item's last reads of the tiles)
   {
-    const unsigned item = item0 + grp;
-    const bool active = item < n;
-    const size_t bi = active ? A.list[item] : 0;
-    const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
-    const int orig = active ? A.raw_qf[bi] : 1;
-    const float* planes[3] = {A.X, A.Y, A.B};
-    const int py = by * 8 + l;
-    float uY[G::VALS];
-    float dcv[3][G::cxb];                    // lane y < cyb: DC row y of the covered blocks
-    float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-    int maxq = 0;
-    const float* wlane = A.w + (size_t)l * G::VALS;      // + c * LANES * VALS
-    // ---- pass A: per channel transform, DC from the lowest frequencies, quant adjust; X and B wait in shared memory
+    constexpr int CR = N / 4;                // 16-byte chunks per tile row; the group's N lanes cover four rows per instruction
+    const int fr = l / CR, fc = l % CR;
+    const bool col_ok = active && 4 * fc < G::C;
+    const size_t off = col_ok ? (size_t)(by * 8 + fr) * fd.pitch + (size_t)bx * 8 + 4 * fc : 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = k == 0 ? 1 : (k == 1 ? 0 : 2);
+      const float* plane = c == 0 ? A.X : (c == 1 ? A.Y : A.B);
+      float* dst = base + c * CG::kSq + fr * P + 4 * fc;
+#pragma unroll
+      for (int i = 0; i < N / 4; ++i) {
+        const bool ok = col_ok && 4 * i + fr < G::R;
+        cp_async16(dst + i * 4 * P, ok ? plane + off + (size_t)(4 * i) * fd.pitch : plane, ok);
+      }
+      cp_async_commit();
+    }
+  }
+  float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+  int maxq = 0;
+  // ---- pass A: per channel transform, DC from the lowest frequencies, quant adjust
 #pragma unroll 1
-    for (int it = 0; it < 3; ++it) {
-      const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
-      float v[N], u[N];
+  for (int it = 0; it < 3; ++it) {
+    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+    float* T = base + c * CG::kSq;
+    if (it == 0) cp_async_wait<2>(); else if (it == 1) cp_async_wait<1>(); else cp_async_wait<0>();
+    SX::sync(bar_id);
+    float u[N];
+    {
+      // rows (lane = pixel row), then columns (lane = horizontal frequency)
+      float v[N];
 #pragma unroll
       for (int j = 0; j < N / 4; ++j) {
-        float4 q4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        // only the transform's own R x C pixels are loaded (the rest of the square stays zero)
-        if (active && l < G::R && 4 * j < G::C) q4 = __ldg(reinterpret_cast<const float4*>(planes[c] + (size_t)py * fd.pitch + bx * 8 + 4 * j));
+        const float4 q4 = *reinterpret_cast<const float4*>(T + l * P + 4 * j);
         v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
       }
-      SX::template forward<MODE>(tbuf, l, col, v, u, bar_id);
-      // lowest frequencies -> DC of the covered blocks (oracle DcFromLowestFrequencies): lane hf < cxb scales its cyb
-      // values and inverts them vertically, lane y < cyb then inverts row y horizontally
-      if (l < G::cxb) {
-        float t[G::cyb];
-#pragma unroll
-        for (int vf = 0; vf < G::cyb; ++vf) t[vf] = u[vf] * resample_scale(G::R, vf) * resample_scale(G::C, l);
-        idct1d<G::cyb>(t);
-#pragma unroll
-        for (int y = 0; y < G::cyb; ++y) llf[c * 64 + y * G::cxb + l] = t[y];
+      if (l < G::R) {   // (the other rows are zero and stay zero)
+        if constexpr (MODE == kModeTall2) dct1d<N / 2>(v);
+        else if constexpr (MODE == kModeTall4) dct1d<N / 4>(v);
+        else dct1d<N>(v);
       }
-      SX::sync(bar_id);
-      if (l < G::cyb) {
-        float t[G::cxb];
 #pragma unroll
-        for (int x = 0; x < G::cxb; ++x) t[x] = llf[c * 64 + l * G::cxb + x];
-        idct1d<G::cxb>(t);
-#pragma unroll
-        for (int x = 0; x < G::cxb; ++x) dcv[c][x] = t[x];
-      }
-      if (A.adjust) {
-        float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-        const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
-        const int q = adjust_quant_sq<N, MODE>(u, wlane + (size_t)c * G::LANES * G::VALS, c, scale, mulc, orig, thr, l, owner, xch, bar_id);
-        maxq = max(maxq, q);
-        if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
-      }
-      if (it == 0) {
-#pragma unroll
-        for (int j = 0; j < G::VALS; ++j) uY[j] = u[j];
-      } else {
-        float* st = stash[it - 1];
-#pragma unroll
-        for (int j = 0; j < G::VALS; ++j) st[j * N + l] = u[j];   // lane-private column: no barrier needed
-      }
+      for (int j = 0; j < N / 4; ++j) *reinterpret_cast<float4*>(T + l * P + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
-    int quant = orig;
+    SX::sync(bar_id);
+#pragma unroll
+    for (int y = 0; y < N; ++y) u[y] = T[y * P + l];
+    if (owner) {
+      if constexpr (MODE == kModeWide2) dct1d<N / 2>(u);
+      else if constexpr (MODE == kModeWide4) dct1d<N / 4>(u);
+      else dct1d<N>(u);
+    }
+    // lowest frequencies -> DC of the covered blocks (oracle DcFromLowestFrequencies): lane hf < cxb scales its cyb
+    // values and inverts them vertically, lane y < cyb then inverts row y horizontally
+    float* lc = llf + c * (G::cxb * G::cyb);
+    if (l < G::cxb) {
+      float t[G::cyb];
+#pragma unroll
+      for (int vf = 0; vf < G::cyb; ++vf) t[vf] = u[vf] * resample_scale(G::R, vf) * resample_scale(G::C, l);
+      idct1d<G::cyb>(t);
+#pragma unroll
+      for (int y = 0; y < G::cyb; ++y) lc[y * G::cxb + l] = t[y];
+    }
+    SX::sync(bar_id);                        // (every lane has also read its column by now: the tile can take the coefficients)
+    if (l < G::cyb) {
+      float t[G::cxb];
+#pragma unroll
+      for (int x = 0; x < G::cxb; ++x) t[x] = lc[l * G::cxb + x];
+      idct1d<G::cxb>(t);
+#pragma unroll
+      for (int x = 0; x < G::cxb; ++x) lc[l * G::cxb + x] = t[x];     // the DC values of block row l
+    }
+    if (owner) {
+#pragma unroll
+      for (int j = 0; j < G::VALS / 4; ++j) *reinterpret_cast<float4*>(T + l * P + 4 * j) = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+    }
     if (A.adjust) {
-      // every lane computed the same maximum (the sums are group-wide); the group's lanes 0 hold the transform's value
-      quant = maxq;
-    } else { thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f; }
-    // ---- DC values and the integer quant field of the covered blocks
-    if (active && l < G::cyb) {
-#pragma unroll
-      for (int x = 0; x < G::cxb; ++x) {
-        const size_t bj = bi + (size_t)l * fd.bxs + x;
-        store_dc(A, bj, dcv[0][x], dcv[1][x], dcv[2][x]);
-        A.raw_qf[bj] = quant;
-      }
-    }
-    // ---- pass B: quantise Y; its dequantised value feeds X and B; non-zero values are scattered in scan order
-    const float qac = scale * (float)quant;
-    const float inv_qac = inv_gs / (float)quant;
-    const int tx = bx >> 3, ty = by >> 3;
-    const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
-    const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
-    const uint16_t* invrow = A.inv + (size_t)l * G::VALS;
-    const float* dqY = A.dq + (size_t)1 * G::LANES * G::VALS + (size_t)l * G::VALS;
-    constexpr int log2n = G::ncov == 2 ? 1 : (G::ncov == 4 ? 2 : (G::ncov == 8 ? 3 : (G::ncov == 16 ? 4 : (G::ncov == 32 ? 5 : 6))));
-#pragma unroll 1
-    for (int it = 0; it < 3; ++it) {
-      const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
-      const int slot = it;
       float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
-      if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
-      else if (G::xs * G::ys >= 4) {
+      const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+      const int q = adjust_quant_sq<N, MODE>(T + l * P, A.w + (size_t)c * G::LANES * G::VALS + (size_t)l * 4, c, scale, mulc, orig, thr, l, owner, xch, bar_id);
+      maxq = max(maxq, q);
+      if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
+    }
+  }
+  int quant = orig;
+  if (A.adjust) {
+    // every lane computed the same maximum (the sums are group-wide)
+    quant = maxq;
+  } else { thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f; }
+  // ---- DC values and the integer quant field of the covered blocks
+  SX::sync(bar_id);
+  if (active && l < G::cyb) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { thr[i] -= 0.00744f * (float)(G::xs * G::ys); if (thr[i] < 0.5f) thr[i] = 0.5f; }
-      }
-      const float qac_mul = qac * (c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul));
-      const float factor = c == 0 ? x_factor : b_factor;
-      const float* wrow = wlane + (size_t)c * G::LANES * G::VALS;
-      const float* st = stash[it == 0 ? 0 : it - 1];
-      int nz = 0, last = 0;
-      if (owner) {
+    for (int x = 0; x < G::cxb; ++x) {
+      const size_t bj = bi + (size_t)l * fd.bxs + x;
+      const int o = l * G::cxb + x;
+      store_dc(A, bj, llf[0 * (G::cxb * G::cyb) + o], llf[1 * (G::cxb * G::cyb) + o], llf[2 * (G::cxb * G::cyb) + o]);
+      A.raw_qf[bj] = quant;
+    }
+  }
+  // ---- pass B: quantise Y; its dequantised value feeds X and B; non-zero values are scattered in scan order
+  const float qac = scale * (float)quant;
+  const float inv_qac = inv_gs / (float)quant;
+  const int tx = bx >> 3, ty = by >> 3;
+  const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
+  const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
+  const uint16_t* invl = A.inv + (size_t)l * 4;
+  const float* dqY = A.dq + (size_t)1 * G::LANES * G::VALS + (size_t)l * 4;
+  float* rowY = base + 1 * CG::kSq + l * P;
+  constexpr int log2n = G::ncov == 2 ? 1 : (G::ncov == 4 ? 2 : (G::ncov == 8 ? 3 : (G::ncov == 16 ? 4 : (G::ncov == 32 ? 5 : 6))));
+  constexpr int log2cxb = G::cxb == 1 ? 0 : (G::cxb == 2 ? 1 : (G::cxb == 4 ? 2 : 3));
+  // (a transform never straddles an AC group: its blocks share the group, block jj sits jj / cxb rows and jj % cxb columns in)
+  const size_t blk0 = (size_t)((by >> 5) * fd.gxs + (bx >> 5)) * kGroupBlocks + (size_t)(by & 31) * 32 + (bx & 31);
+  const bool first = G::kWide ? (l < G::W / 2) : (l < G::HS / 2);
+#pragma unroll 1
+  for (int it = 0; it < 3; ++it) {
+    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+    const int slot = it;
+    float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+    if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
+    else if (G::xs * G::ys >= 4) {
 #pragma unroll
-        for (int j4 = 0; j4 < G::VALS; j4 += 4) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + j4));
-          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-          const uint2 i4 = __ldg(reinterpret_cast<const uint2*>(invrow + j4));
-          const uint32_t iv[4] = {i4.x & 0xFFFFu, i4.x >> 16, i4.y & 0xFFFFu, i4.y >> 16};
-          float4 d4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          if (c == 1) d4 = __ldg(reinterpret_cast<const float4*>(dqY + j4));
-          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      for (int i = 0; i < 4; ++i) { thr[i] -= 0.00744f * (float)(G::xs * G::ys); if (thr[i] < 0.5f) thr[i] = 0.5f; }
+    }
+    const float thrA = G::kWide ? (first ? thr[0] : thr[1]) : (first ? thr[0] : thr[2]);
+    const float thrB = G::kWide ? (first ? thr[2] : thr[3]) : (first ? thr[1] : thr[3]);
+    const float qac_mul = qac * (c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul));
+    const float factor = c == 0 ? x_factor : b_factor;
+    const float* wl = A.w + (size_t)c * G::LANES * G::VALS + (size_t)l * 4;
+    const float* row = base + c * CG::kSq + l * P;
+    int16_t* cdst = A.coeffs + (blk0 * 3 + slot) * 64;
+    int nz = 0, last = 0;
+    if (owner) {
+#pragma unroll 1
+      for (int j4 = 0; j4 < G::VALS; j4 += 4) {
+        const size_t co = (size_t)(j4 >> 2) * G::LANES * 4;
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wl + co));
+        const uint2 i4 = __ldg(reinterpret_cast<const uint2*>(invl + co));
+        const float4 y4 = *reinterpret_cast<const float4*>(rowY + j4);
+        float4 d4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), s4 = y4;
+        if (c == 1) d4 = __ldg(reinterpret_cast<const float4*>(dqY + co));
+        else s4 = *reinterpret_cast<const float4*>(row + j4);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float yv[4] = {y4.x, y4.y, y4.z, y4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        const uint32_t iv[4] = {i4.x & 0xFFFFu, i4.x >> 16, i4.y & 0xFFFFu, i4.y >> 16};
+        const float t = j4 >= G::VALS / 2 ? thrB : thrA;
+        float deq[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = j4 + e;
-            const int x = G::kWide ? l : j, y = G::kWide ? j : l;
-            float in;
-            if (c == 1) in = uY[j];
-            else in = __fmaf_rn(-factor, uY[j], st[j * N + l]);          // uY holds the dequantised Y by now
-            const float t = thr[(y >= G::HS / 2 ? 2 : 0) + (x >= G::W / 2 ? 1 : 0)];
-            const float val = (wv[e] * qac_mul) * in;
-            int q = (fabsf(val) >= t) ? (int)rintf(val) : 0;
-            if (x < G::xs && y < G::ys) q = 0;
-            q = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
-            if (c == 1) uY[j] = (quant_bias(1, q) * dv[e]) * inv_qac;
-            if (q != 0 && active) {
-              const int k = (int)iv[e];
-              const int jj = k >> 6;
-              const int cbx = bx + (jj % G::cxb), cby = by + (jj / G::cxb);
-              const int g = (cby >> 5) * fd.gxs + (cbx >> 5);
-              const size_t blk = (size_t)g * kGroupBlocks + (size_t)(cby & 31) * 32 + (cbx & 31);
-              A.coeffs[(blk * 3 + slot) * 64 + (k & 63)] = (int16_t)q;
-              ++nz; last = max(last, k);
-            }
+        for (int e = 0; e < 4; ++e) {
+          const int j = j4 + e;
+          const int x = G::kWide ? l : j, y = G::kWide ? j : l;
+          float in;
+          if (c == 1) in = yv[e];
+          else in = __fmaf_rn(-factor, yv[e], sv[e]);                   // the Y row holds the dequantised Y by now
+          const float val = (wv[e] * qac_mul) * in;
+          int q = (fabsf(val) >= t) ? (int)rintf(val) : 0;
+          if (x < G::xs && y < G::ys) q = 0;
+          q = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
+          deq[e] = c == 1 ? (quant_bias(1, q) * dv[e]) * inv_qac : 0.0f;
+          if (q != 0 && active) {
+            const int k = (int)iv[e];
+            const int jj = k >> 6;
+            cdst[(size_t)((jj >> log2cxb) * 32 + (jj & (G::cxb - 1))) * 192 + (k & 63)] = (int16_t)q;
+            ++nz; last = max(last, k);
           }
         }
-      }
-      float cnt[1] = {(float)nz};                                       // <= 4096: exact in float
-      lane_sums<N, G::LANES, 1>(cnt, xch, l, bar_id);
-      float lastf[1] = {(float)last};
-      lane_maxs<N, G::LANES, 1>(lastf, xch, l, bar_id);
-      if (active && l == 0) {
-        const int nzt = (int)cnt[0];
-        const int shared = (nzt + G::ncov - 1) >> log2n;
-        A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nzt;
-        A.lastk[(size_t)c * nblk + bi] = (uint16_t)(int)lastf[0];
-        for (int jj = 0; jj < G::ncov; ++jj) A.nzeros[(size_t)c * nblk + bi + (size_t)(jj / G::cxb) * fd.bxs + (jj % G::cxb)] = (uint8_t)shared;
+        if (c == 1) *reinterpret_cast<float4*>(rowY + j4) = make_float4(deq[0], deq[1], deq[2], deq[3]);
       }
     }
-    SX::sync(bar_id);   // buffers are reused by the next item
+    float cnt[1] = {(float)nz};                                       // <= 4096: exact in float
+    lane_sums<N, G::LANES, 1>(cnt, xch, l, bar_id);
+    float lastf[1] = {(float)last};
+    lane_maxs<N, G::LANES, 1>(lastf, xch, l, bar_id);
+    if (active && l == 0) {
+      const int nzt = (int)cnt[0];
+      const int shared = (nzt + G::ncov - 1) >> log2n;
+      A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nzt;
+      A.lastk[(size_t)c * nblk + bi] = (uint16_t)(int)lastf[0];
+      for (int jj = 0; jj < G::ncov; ++jj) A.nzeros[(size_t)c * nblk + bi + (size_t)(jj / G::cxb) * fd.bxs + (jj % G::cxb)] = (uint8_t)shared;
+    }
   }
 }
 
@@ -657,7 +714,7 @@ __global__ void __launch_bounds__(64) k_coeff8_all(CoeffAllArgs AA) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(128) k_coeffsq_all(CoeffAllArgs AA) {
+__global__ void __launch_bounds__(CoeffSqGeom<N>::kThreads) k_coeffsq_all(CoeffAllArgs AA) {
   using CG = CoeffSqGeom<N>;
   extern __shared__ __align__(16) float smem_f[];
   constexpr int first = N == 16 ? kList16Tall : (N == 32 ? kList32Tall : kList64Tall);   // tall, wide, square
@@ -698,7 +755,7 @@ static void launch_coeffsq_all(const CoeffAllArgs& AA, cudaStream_t s) {
   size_t grid = (max_items + CG::kGroups - 1) / CG::kGroups;
   if (grid > 148 * 8) grid = 148 * 8;
   ++g_kernel_launches;
-  k_coeffsq_all<N><<<(unsigned)grid, 128, smem, s>>>(AA);
+  k_coeffsq_all<N><<<(unsigned)grid, CG::kThreads, smem, s>>>(AA);
 }
 
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
@@ -717,17 +774,8 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
   // tables in lane order per list; inv_order: [order class] natural, [13..15] transposed for the wide strategy of class 4 / 6 / 8
   const int kind8[6] = {0, 1, 2, 3, 9, 9};
   for (int li = 0; li < 6; ++li) { AA.w[li] = T.w[kind8[li]]; AA.dq[li] = T.dq[kind8[li]]; AA.inv[li] = nullptr; }
-  AA.w[kList16Tall] = T.w[6]; AA.dq[kList16Tall] = T.dq[6]; AA.inv[kList16Tall] = inv_order[4];
-  AA.w[kList16Wide] = T.wT[6]; AA.dq[kList16Wide] = T.dqT[6]; AA.inv[kList16Wide] = inv_order[13];
-  AA.w[kList16Sq] = T.w[4]; AA.dq[kList16Sq] = T.dq[4]; AA.inv[kList16Sq] = inv_order[2];
-  AA.w[kList32Tall] = T.w[8]; AA.dq[kList32Tall] = T.dq[8]; AA.inv[kList32Tall] = inv_order[6];
-  AA.w[kList32Wide] = T.wT[8]; AA.dq[kList32Wide] = T.dqT[8]; AA.inv[kList32Wide] = inv_order[14];
-  AA.w[kList32Sq] = T.w[5]; AA.dq[kList32Sq] = T.dq[5]; AA.inv[kList32Sq] = inv_order[3];
-  AA.w[kList64Tall] = T.w[12]; AA.dq[kList64Tall] = T.dq[12]; AA.inv[kList64Tall] = inv_order[8];
-  AA.w[kList64Wide] = T.wT[12]; AA.dq[kList64Wide] = T.dqT[12]; AA.inv[kList64Wide] = inv_order[15];
-  AA.w[kList64Sq] = T.w[11]; AA.dq[kList64Sq] = T.dq[11]; AA.inv[kList64Sq] = inv_order[7];
-  AA.w[kList32Tall4] = T.w[7]; AA.dq[kList32Tall4] = T.dq[7]; AA.inv[kList32Tall4] = inv_order[5];
-  AA.w[kList32Wide4] = T.wT[7]; AA.dq[kList32Wide4] = T.dqT[7]; AA.inv[kList32Wide4] = inv_order[16];
+  // 16 / 32 / 64-sized lists: tables and inverse scan orders in 16-byte chunks, [c][chunk][lane][4] (AcsTables::wJ)
+  for (int li = kList16Tall; li < kNumLists; ++li) { AA.w[li] = T.wJ[li - kList16Tall]; AA.dq[li] = T.dqJ[li - kList16Tall]; AA.inv[li] = T.invJ[li - kList16Tall]; }
   ++g_kernel_launches;
   size_t g8 = (nblk + 63) / 64 + 6;
   if (g8 > 148 * 16) g8 = 148 * 16;

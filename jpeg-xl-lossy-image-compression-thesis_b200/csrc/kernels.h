@@ -40,6 +40,9 @@ struct AcsParams {
 struct AcsTables {
   const float* w[17]; const float* dq[17]; const float* wT[17]; const float* dqT[17]; const float* w8[4]; const float* dq8[4];
   const float* wC[6]; const float* dqC[6];
+  // the coefficient stage's 16 / 32 / 64-sized strategies (k_coeff.cu list order from kList16Tall on): quantisation
+  // tables and inverse scan orders in lane order and 16-byte chunks, [c][chunk][lane][4]
+  const float* wJ[11]; const float* dqJ[11]; const uint16_t* invJ[11];
 };
 size_t acs_work_floats(const FrameDim& fd);   // candidate-value tables of the search
 size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-aligned squares (uint32 words)

@@ -396,6 +396,15 @@ template <int S> __device__ __forceinline__ void inv8x8(float* c, float* p) {
   }
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS); !valid zero-fills the destination (source size 0)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 // ====================================================================================================
 // N x N squares, N lanes.  MODE: one square transform, two tall halves (left | right, N rows x N/2 columns
 // each) or two wide halves (top / bottom, N/2 rows x N columns each).

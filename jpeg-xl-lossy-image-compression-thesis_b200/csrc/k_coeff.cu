@@ -173,6 +173,13 @@ constexpr Zigzag8 make_zigzag8() {
   return z;
 }
 __device__ constexpr Zigzag8 kZigzag8 = make_zigzag8();
+constexpr Zigzag8 make_inv_zigzag8() {
+  const Zigzag8 z = make_zigzag8();
+  Zigzag8 inv{};
+  for (int k = 0; k < 64; ++k) inv.pos[z.pos[k]] = k;
+  return inv;
+}
+__device__ constexpr Zigzag8 kInvZigzag8 = make_inv_zigzag8();   // storage position -> scan index
 
 // oracle QuantizeBlockAC for an 8x8 block in registers; returns the values in place (as ints)
 __device__ __forceinline__ void quantize8(const float* cf, const float* __restrict__ qm, float qac_mul, const float thr[4], int* out) {
@@ -318,6 +325,200 @@ __device__ __noinline__ void coeff8_body(const CoeffArgs& A, unsigned i) {
     int q[64];
     quantize8(cf, A.w + c * 64, qac * (c == 0 ? A.x_qm_mul : A.b_qm_mul), thr, q);
     emit8(A, q, cblk, c == 0 ? 1 : 2, c, bi, nblk);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 8x8, eight lanes per block
+// DCT, DCT4X4, DCT4X8 and DCT8X4 (the bulk of a searched frame's 8x8 blocks) run with eight lanes per block, four blocks
+// per warp — the geometry of k_acs_evalsq<8>: lane (q * 4 + hf) of a block owns the eight coefficients storage_index()
+// gives it (oracle/jxo_acs.cc), three channels of them stay in registers, and the code of a strategy is a few hundred
+// instructions.  (The one-thread-per-block version ran 5 800 instructions once per thread and spent 58 % of its stall
+// samples on instruction fetches: ncu, profiles/r02k.)  A group's tile is 8 rows x 12 floats, 104 floats from the next
+// group's: row accesses (16 bytes) and column accesses of the warp's four groups are conflict-free.
+constexpr int kC8Pitch = 12, kC8Tile = 104, kC8WarpFloats = 3 * 4 * kC8Tile + 4 * 32;   // tiles [c][group], then 64 int16 per group
+
+template <int S> __device__ __forceinline__ int pos8_of(int l, int j) {   // storage position of a lane's j-th value
+  if constexpr (S == kStratDCT) return l * 8 + j;
+  else if constexpr (S == kStratDCT4X4) return ((j >> 2) + (l & 3) * 2) * 8 + (l >> 2) + (j & 3) * 2;
+  else if constexpr (S == kStratDCT4X8) return ((l >> 2) + (l & 3) * 2) * 8 + j;
+  else return ((j >> 2) + (j & 3) * 2) * 8 + l;                              // DCT8X4
+}
+
+// rows, then columns, then the DC Hadamard of the split strategies (same operations as k_acs_evalsq<8>'s forward half)
+template <int S>
+__device__ __forceinline__ void fwd8_lanes(float* t, int l, float (&v)[8]) {
+  constexpr bool row_full = S == kStratDCT || S == kStratDCT8X4, col_full = S == kStratDCT || S == kStratDCT4X8;
+  constexpr int P = kC8Pitch;
+  {
+    const float4 a = *reinterpret_cast<const float4*>(t + l * P), b = *reinterpret_cast<const float4*>(t + l * P + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+  if constexpr (row_full) dct1d<8>(v); else { dct1d<4>(v); dct1d<4>(v + 4); }
+  *reinterpret_cast<float4*>(t + l * P) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(t + l * P + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  __syncwarp();
+#pragma unroll
+  for (int y = 0; y < 8; ++y) v[y] = t[y * P + l];
+  if constexpr (col_full) dct1d<8>(v); else { dct1d<4>(v); dct1d<4>(v + 4); }
+  if constexpr (S != kStratDCT) {
+    const float pa = __shfl_xor_sync(0xffffffffu, v[0], 4), pb = __shfl_xor_sync(0xffffffffu, v[4], 4);
+    if constexpr (S == kStratDCT4X8) {
+      if (l == 0) v[0] = (v[0] + pa) * 0.5f; else if (l == 4) v[0] = (pa - v[0]) * 0.5f;
+    } else if constexpr (S == kStratDCT8X4) {
+      if (l == 0) { const float b0 = v[0], b1 = v[4]; v[0] = (b0 + b1) * 0.5f; v[4] = (b0 - b1) * 0.5f; }
+    } else {
+      if (l == 0) { const float b00 = v[0], b01 = pa, b10 = v[4], b11 = pb; v[0] = (b00 + b01 + b10 + b11) * 0.25f; v[4] = (b00 - b01 + b10 - b11) * 0.25f; }
+      else if (l == 4) { const float b00 = pa, b01 = v[0], b10 = pb, b11 = v[4]; v[0] = (b00 + b01 - b10 - b11) * 0.25f; v[4] = (b00 - b01 - b10 + b11) * 0.25f; }
+    }
+  }
+}
+
+// oracle AdjustQuantBlockAC for the plain 8x8 DCT, lane = storage row (adjust_quant8 with the rows spread over the lanes)
+__device__ __forceinline__ int adjust_quant8_lanes(const float (&cf)[8], const float* __restrict__ wrow, int c, float scale, float qm_mul,
+                                                   int quant, float thr[4], int l) {
+  const float qac = scale * (float)quant;
+  const bool first = l < 4;
+  const float thrA = first ? thr[0] : thr[2], thrB = first ? thr[1] : thr[3];
+  float a_hf = 0.0f, a_err = 0.0f, a_vals = 0.0f, nzA = 0.0f, nzB = 0.0f, meA = 0.0f, meB = 0.0f;
+  const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow)), w1 = __ldg(reinterpret_cast<const float4*>(wrow + 4));
+  const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    if (x == 0 && l == 0) continue;
+    const bool second = x >= 4;
+    const float val = cf[x] * (wv[x] * qac * qm_mul);
+    const float v = (fabsf(val) < (second ? thrB : thrA)) ? 0.0f : rintf(val);
+    const float err = fabsf(val - v);
+    a_err += err;
+    a_vals += fabsf(v);
+    if (c == 1 && v == 0.0f) { if (second) { if (meB < err) meB = err; } else { if (meA < err) meA = err; } }
+    if (v != 0.0f) {
+      if (second) nzB += fabsf(v); else nzA += fabsf(v);
+      const bool in_corner = l >= 7 && x >= 7;
+      const bool on_border = l == 7 || x == 7;
+      const bool in_larger_corner = x >= 4 && l >= 4;
+      if (in_corner || (on_border && in_larger_corner)) a_hf += fabsf(val);
+    }
+  }
+  const float r_hf = group_sum<8>(a_hf), r_err = group_sum<8>(a_err), r_vals = group_sum<8>(a_vals);
+  const float hfNZ[4] = {group_sum<8>(first ? nzA : 0.0f), group_sum<8>(first ? nzB : 0.0f), group_sum<8>(first ? 0.0f : nzA),
+                         group_sum<8>(first ? 0.0f : nzB)};
+  float hfME[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (c == 1) {
+    hfME[0] = group_fmax<8>(first ? meA : 0.0f); hfME[1] = group_fmax<8>(first ? meB : 0.0f);
+    hfME[2] = group_fmax<8>(first ? 0.0f : meA); hfME[3] = group_fmax<8>(first ? 0.0f : meB);
+  }
+  return adjust_close<kStratDCT>(c, quant, 1, r_hf, r_err, r_vals, hfNZ, hfME, thr);
+}
+
+// one round of a warp: four list entries (blocks), eight lanes each
+template <int S>
+__device__ __noinline__ void coeff8_lanes_body(const CoeffArgs& A, float* smem_w, unsigned item0) {
+  constexpr int P = kC8Pitch;
+  const FrameDim& fd = A.fd;
+  const int lane = threadIdx.x & 31, l = lane & 7, grp = lane >> 3;
+  const unsigned n = *A.count;
+  const unsigned item = item0 + grp;
+  const bool active = item < n;
+  const size_t nblk = (size_t)fd.bxs * fd.bys;
+  const size_t bi = active ? A.list[item] : 0;
+  const int bx = (int)(bi % fd.bxs), by = (int)(bi / fd.bxs);
+  const float scale = A.qd->scale, inv_gs = A.qd->inv_global_scale;
+  const int orig = active ? A.raw_qf[bi] : 1;
+  int16_t* stage = reinterpret_cast<int16_t*>(smem_w + 3 * 4 * kC8Tile) + grp * 64;
+  __syncwarp();                                // (the previous round's reads of the tiles)
+  {
+    // the group's eight lanes fetch their block: two 16-byte chunks per row, four rows per instruction
+    const int fr = l >> 1, fc = l & 1;
+    const size_t off = active ? (size_t)(by * 8 + fr) * fd.pitch + (size_t)bx * 8 + 4 * fc : 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int c = k == 0 ? 1 : (k == 1 ? 0 : 2);
+      const float* plane = c == 0 ? A.X : (c == 1 ? A.Y : A.B);
+      float* dst = smem_w + (c * 4 + grp) * kC8Tile + fr * P + 4 * fc;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) cp_async16(dst + i * 4 * P, active ? plane + off + (size_t)(4 * i) * fd.pitch : plane, active);
+    }
+    cp_async_commit();
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  float cf[3][8];
+  float thr_y[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+  int maxq = 0;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+    fwd8_lanes<S>(smem_w + (c * 4 + grp) * kC8Tile, l, cf[c]);
+    if (S == kStratDCT && A.adjust) {
+      float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+      const float mulc = c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul);
+      maxq = max(maxq, adjust_quant8_lanes(cf[c], A.w + c * 64 + l * 8, c, scale, mulc, orig, thr, l));
+      if (c == 1) { thr_y[0] = thr[0]; thr_y[1] = thr[1]; thr_y[2] = thr[2]; thr_y[3] = thr[3]; }
+    }
+  }
+  int quant = orig;
+  if (A.adjust) { if (S == kStratDCT) quant = maxq; }
+  else { thr_y[0] = 0.56f; thr_y[1] = thr_y[2] = thr_y[3] = 0.62f; }
+  {
+    // the DC values sit in lane 0's first coefficient
+    const float dX = __shfl_sync(0xffffffffu, cf[0][0], grp * 8), dY = __shfl_sync(0xffffffffu, cf[1][0], grp * 8),
+                dB = __shfl_sync(0xffffffffu, cf[2][0], grp * 8);
+    if (active && l == 0) { store_dc(A, bi, dX, dY, dB); A.raw_qf[bi] = quant; }
+  }
+  // ---- quantise Y, roundtrip it, remove the chroma-from-luma share from X and B, quantise them
+  const float qac = scale * (float)quant;
+  const float inv_qac = inv_gs / (float)quant;
+  const size_t cblk = (size_t)((by >> 5) * fd.gxs + (bx >> 5)) * kGroupBlocks + (size_t)(by & 31) * 32 + (bx & 31);
+  const int tx = bx >> 3, ty = by >> 3;
+  const float x_factor = 0.0f + (float)A.cmap[(size_t)ty * fd.txs + tx] / 84.0f;
+  const float b_factor = 1.0f + (float)A.cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] / 84.0f;
+  float ydq[8];
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const int c = it == 0 ? 1 : (it == 1 ? 0 : 2);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(A.w + c * 64 + l * 8)), w1 = __ldg(reinterpret_cast<const float4*>(A.w + c * 64 + l * 8 + 4));
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float qac_mul = qac * (c == 0 ? A.x_qm_mul : (c == 1 ? 1.0f : A.b_qm_mul));
+    const float factor = c == 0 ? x_factor : b_factor;
+    float thr[4] = {0.58f, 0.64f, 0.64f, 0.64f};
+    if (c == 1) { thr[0] = thr_y[0]; thr[1] = thr_y[1]; thr[2] = thr_y[2]; thr[3] = thr_y[3]; }
+    int nz = 0, last = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pos = pos8_of<S>(l, j);
+      const int y = pos >> 3, x = pos & 7;
+      const bool yh = y >= 4, xh = x >= 4;
+      const float t = yh ? (xh ? thr[3] : thr[2]) : (xh ? thr[1] : thr[0]);
+      const float in = c == 1 ? cf[1][j] : __fmaf_rn(-factor, ydq[j], cf[c][j]);
+      const float val = (wv[j] * qac_mul) * in;
+      int q = (fabsf(val) >= t) ? (int)rintf(val) : 0;
+      if (pos == 0) q = 0;
+      q = q > 32767 ? 32767 : (q < -32767 ? -32767 : q);
+      const int k = kInvZigzag8.pos[pos];
+      stage[k] = (int16_t)q;
+      if (q != 0) { ++nz; last = max(last, k); }
+      if (c == 1) cf[1][j] = (float)q;       // (kept for the roundtrip below)
+    }
+    if (c == 1) {
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(A.dq + 64 + l * 8)), d1 = __ldg(reinterpret_cast<const float4*>(A.dq + 64 + l * 8 + 4));
+      const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ydq[j] = (quant_bias(1, (int)cf[1][j]) * dv[j]) * inv_qac;
+    }
+    nz = group_isum<8>(nz);
+    last = group_imax<8>(last);
+    __syncwarp();
+    if (active) {
+      // scan-order output of the block's channel: 128 contiguous bytes, 16 per lane
+      reinterpret_cast<uint4*>(A.coeffs + (cblk * 3 + it) * 64)[l] = reinterpret_cast<const uint4*>(stage)[l];
+      if (l == 0) {
+        A.nzcount[(size_t)c * nblk + bi] = (uint16_t)nz;
+        A.lastk[(size_t)c * nblk + bi] = (uint16_t)last;
+        A.nzeros[(size_t)c * nblk + bi] = (uint8_t)nz;
+      }
+    }
+    __syncwarp();                              // `stage` is rewritten by the next channel
   }
 }
 
@@ -691,25 +892,39 @@ __device__ __forceinline__ CoeffArgs list_args(const CoeffAllArgs& AA, int li) {
   return A;
 }
 
-__global__ void __launch_bounds__(64) k_coeff8_all(CoeffAllArgs AA) {
-  unsigned ctas[6], total = 0;
+// DCT2X2 and IDENTITY (rare; not separable along lanes): one thread per block
+__global__ void __launch_bounds__(64) k_coeff8_special(CoeffAllArgs AA) {
+  unsigned ctas[2], total = 0;
 #pragma unroll
-  for (int li = 0; li < 6; ++li) { ctas[li] = (AA.lists[li] + 63) / 64; total += ctas[li]; }
+  for (int m = 0; m < 2; ++m) { ctas[m] = (AA.lists[kListID + m] + 63) / 64; total += ctas[m]; }
+  for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
+    const int m = v >= ctas[0] ? 1 : 0;
+    const unsigned i = (v - (m ? ctas[0] : 0)) * 64 + threadIdx.x;
+    if (i >= AA.lists[kListID + m]) continue;
+    const CoeffArgs A = list_args(AA, kListID + m);
+    if (m == 0) coeff8_body<kStratIDENTITY>(A, i); else coeff8_body<kStratDCT2X2>(A, i);
+  }
+}
+
+// DCT, DCT4X4, DCT4X8, DCT8X4: a warp takes four list entries per round; virtual CTAs of 16 entries walk the lists
+__global__ void __launch_bounds__(128) k_coeff8_lanes(CoeffAllArgs AA) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int lists[4] = {kListDCT, kList4X4, kList4X8, kList8X4};
+  unsigned ctas[4], total = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { ctas[m] = (AA.lists[lists[m]] + 15) / 16; total += ctas[m]; }
+  float* smem_w = smem_f + (threadIdx.x >> 5) * kC8WarpFloats;
   for (unsigned v = blockIdx.x; v < total; v += gridDim.x) {
     unsigned rel = v;
-    int li = 0;
-    while (rel >= ctas[li]) { rel -= ctas[li]; ++li; }
-    const unsigned i = rel * 64 + threadIdx.x;
-    if (i >= AA.lists[li]) continue;
-    const CoeffArgs A = list_args(AA, li);
-    switch (li) {
-      case kListDCT: coeff8_body<kStratDCT>(A, i); break;
-      case kListID: coeff8_body<kStratIDENTITY>(A, i); break;
-      case kList2X2: coeff8_body<kStratDCT2X2>(A, i); break;
-      case kList4X4: coeff8_body<kStratDCT4X4>(A, i); break;
-      case kList4X8: coeff8_body<kStratDCT4X8>(A, i); break;
-      default: coeff8_body<kStratDCT8X4>(A, i); break;
-    }
+    int m = 0;
+    while (rel >= ctas[m]) { rel -= ctas[m]; ++m; }
+    const unsigned item0 = rel * 16 + (threadIdx.x >> 5) * 4;
+    if (item0 >= AA.lists[lists[m]]) continue;       // (warp-uniform)
+    const CoeffArgs A = list_args(AA, lists[m]);
+    if (m == 0) coeff8_lanes_body<kStratDCT>(A, smem_w, item0);
+    else if (m == 1) coeff8_lanes_body<kStratDCT4X4>(A, smem_w, item0);
+    else if (m == 2) coeff8_lanes_body<kStratDCT4X8>(A, smem_w, item0);
+    else coeff8_lanes_body<kStratDCT8X4>(A, smem_w, item0);
   }
 }
 
@@ -772,14 +987,18 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
   A.w = nullptr; A.dq = nullptr; A.inv = nullptr; A.list = nullptr; A.count = nullptr;
   AA.lists = lists; AA.nblk = (unsigned)nblk;
   // tables in lane order per list; inv_order: [order class] natural, [13..15] transposed for the wide strategy of class 4 / 6 / 8
-  const int kind8[6] = {0, 1, 2, 3, 9, 9};
-  for (int li = 0; li < 6; ++li) { AA.w[li] = T.w[kind8[li]]; AA.dq[li] = T.dq[kind8[li]]; AA.inv[li] = nullptr; }
+  // 8x8 lists: DCT, DCT4X4, DCT4X8, DCT8X4 in the lane order of the eight-lane kernel (AcsTables::w8); IDENTITY, DCT2X2 stored order
+  AA.w[kListDCT] = T.w8[0]; AA.dq[kListDCT] = T.dq8[0]; AA.w[kList4X4] = T.w8[1]; AA.dq[kList4X4] = T.dq8[1];
+  AA.w[kList4X8] = T.w8[2]; AA.dq[kList4X8] = T.dq8[2]; AA.w[kList8X4] = T.w8[3]; AA.dq[kList8X4] = T.dq8[3];
+  AA.w[kListID] = T.w[1]; AA.dq[kListID] = T.dq[1]; AA.w[kList2X2] = T.w[2]; AA.dq[kList2X2] = T.dq[2];
+  for (int li = 0; li < 6; ++li) AA.inv[li] = nullptr;
   // 16 / 32 / 64-sized lists: tables and inverse scan orders in 16-byte chunks, [c][chunk][lane][4] (AcsTables::wJ)
   for (int li = kList16Tall; li < kNumLists; ++li) { AA.w[li] = T.wJ[li - kList16Tall]; AA.dq[li] = T.dqJ[li - kList16Tall]; AA.inv[li] = T.invJ[li - kList16Tall]; }
-  ++g_kernel_launches;
-  size_t g8 = (nblk + 63) / 64 + 6;
+  g_kernel_launches += 2;
+  size_t g8 = (nblk + 15) / 16 + 4;
   if (g8 > 148 * 16) g8 = 148 * 16;
-  k_coeff8_all<<<(unsigned)g8, 64, 0, s>>>(AA);
+  k_coeff8_lanes<<<(unsigned)g8, 128, 4 * kC8WarpFloats * sizeof(float), s>>>(AA);
+  k_coeff8_special<<<(unsigned)((nblk + 63) / 64 + 2 > 148 * 8 ? 148 * 8 : (nblk + 63) / 64 + 2), 64, 0, s>>>(AA);
   launch_coeffsq_all<64>(AA, s);     // (longest dependency chains first)
   launch_coeffsq_all<32>(AA, s);
   launch_coeffsq_all<16>(AA, s);

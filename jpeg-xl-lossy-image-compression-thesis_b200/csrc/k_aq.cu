@@ -53,12 +53,27 @@ __global__ void __launch_bounds__(256) k_aq_pre(const float* __restrict__ Y, Fra
   const int t = threadIdx.x;
   const int gx0 = blockIdx.x * 128, gy0 = blockIdx.y * 32;
   const int xs = fd.xs_pad, ys = fd.ys_pad;
-  for (int i = t; i < 34 * 130; i += 256) {
-    const int r = i / 130, c = i % 130;
-    int gy = gy0 + r - 1, gx = gx0 + c - 1;
-    gy = gy < 0 ? 0 : (gy > ys - 1 ? ys - 1 : gy);
-    gx = gx < 0 ? 0 : (gx > xs - 1 ? xs - 1 : gx);
-    sy[r][c] = Y[(size_t)gy * fd.pitch + gx];
+  {
+    // (all of the thread's loads in flight before the first store: the rolled one-load-one-store loop was half of the
+    // kernel's stall samples, profiles/r02k)
+    float tmp[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+      const int i = t + k * 256;
+      tmp[k] = 0.0f;
+      if (i < 34 * 130) {
+        const int r = i / 130, c = i % 130;
+        int gy = gy0 + r - 1, gx = gx0 + c - 1;
+        gy = gy < 0 ? 0 : (gy > ys - 1 ? ys - 1 : gy);
+        gx = gx < 0 ? 0 : (gx > xs - 1 ? xs - 1 : gx);
+        tmp[k] = __ldg(Y + (size_t)gy * fd.pitch + gx);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 18; ++k) {
+      const int i = t + k * 256;
+      if (i < 34 * 130) sy[i / 130][i % 130] = tmp[k];
+    }
   }
   __syncthreads();
   const int cx = t & 31, cy = t >> 5;

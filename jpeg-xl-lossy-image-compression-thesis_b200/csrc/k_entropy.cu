@@ -479,7 +479,15 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   {
     const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
     uint4* dst = reinterpret_cast<uint4*>(s_rmap);
-    for (int i = t; i < K * kAnsTabSize / 8; i += kAnsWarps * 32) dst[i] = src[i];
+    // (eight 16-byte loads in flight per thread: the copy is 192 KB from L2 and every chain of the CTA waits for it)
+    const int n16 = K * kAnsTabSize / 8;
+    for (int i0 = 0; i0 < n16; i0 += 8 * kAnsWarps * 32) {
+      uint4 tmp[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int i = i0 + k * kAnsWarps * 32 + t; if (i < n16) tmp[k] = __ldg(src + i); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int i = i0 + k * kAnsWarps * 32 + t; if (i < n16) dst[i] = tmp[k]; }
+    }
     for (int i = t; i < kNumAcContexts; i += kAnsWarps * 32) s_cmap[i] = cmap_g[i];
   }
   __syncthreads();

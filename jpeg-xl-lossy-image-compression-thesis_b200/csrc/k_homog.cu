@@ -91,20 +91,34 @@ __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X
   const int by = blockIdx.y;
   const int px0 = blockIdx.x * 256;
   const int gy0 = by * 8;
-  // ---- load tiles (0 where the reference would not read) ------------------------------
-  for (int i = t; i < 10 * 258; i += 256) {
-    const int r = i / 258, c = i % 258;
-    const int gy = gy0 + r - 1, gx = px0 + c - 1;
-    float v = 0.0f;
-    if (gy >= 0 && gy < fd.ys_pad && gx >= 0 && gx < fd.pitch) v = Y[(size_t)gy * fd.pitch + gx];
-    sy[r][hidx(c)] = v;
-  }
-  for (int i = t; i < 8 * 256; i += 256) {
-    const int r = i >> 8, c = i & 255;
-    const int gx = px0 + c;
-    float vx = 0.0f, vb = 0.0f;
-    if (gx < fd.pitch) { vx = X[(size_t)(gy0 + r) * fd.pitch + gx]; vb = B[(size_t)(gy0 + r) * fd.pitch + gx]; }
-    sx[r][hidx(c)] = vx; sb[r][hidx(c)] = vb;
+  // ---- load tiles (0 where the reference would not read): thread = column, every load of the thread in flight before the
+  // first store (the rolled one-load-one-store loops waited for 40 % of the kernel's stall samples: profiles/r02k)
+  {
+    const int gx = px0 + t;
+    const bool col_in = gx < fd.pitch;
+    float vy[10], vx[8], vb[8];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const int gy = gy0 + r - 1;
+      vy[r] = (col_in && gy >= 0 && gy < fd.ys_pad) ? __ldg(Y + (size_t)gy * fd.pitch + gx) : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      vx[r] = col_in ? __ldg(X + (size_t)(gy0 + r) * fd.pitch + gx) : 0.0f;
+      vb[r] = col_in ? __ldg(B + (size_t)(gy0 + r) * fd.pitch + gx) : 0.0f;
+    }
+    float halo = 0.0f;                          // columns -1 and 256 of the Y tile: threads 0..19 = (row, side)
+    const int hr = t >> 1, hc = (t & 1) ? 257 : 0;
+    if (t < 20) {
+      const int gy = gy0 + hr - 1, hx = px0 + hc - 1;
+      if (gy >= 0 && gy < fd.ys_pad && hx >= 0 && hx < fd.pitch) halo = __ldg(Y + (size_t)gy * fd.pitch + hx);
+    }
+    const int ci = hidx(t), cy = hidx(t + 1);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) sy[r][cy] = vy[r];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { sx[r][ci] = vx[r]; sb[r][ci] = vb[r]; }
+    if (t < 20) sy[hr][hidx(hc)] = halo;
   }
   __syncthreads();
   float thr = 0.25f;

@@ -50,7 +50,7 @@ STAGE_BYTES_PER_PX = {"xyb": 15.0, "aq": 12.1, "homog": 12.2, "coeff": 18.3}
 # the search workloads' coefficient stage is a dozen launches (one per strategy), no single capture applies: null
 TRAFFIC_BYTES_K7_DCT8_4K = 120.4e6
 PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9   # issue slots of the GPU: 148 SMs x 4 schedulers x max SM clock
-ACS_WARP_INST_PER_PX = 110.5   # search kernels, warp instructions per pixel at 1080p combined d = 1 (profiles/r02e_inst_1080p.csv)
+ACS_WARP_INST_PER_PX = 106.0   # search kernels, warp instructions per pixel at 1080p combined d = 1 (profiles/r02m_launches_1080p.csv: 219.8 M per frame)
 STAGE_INDEX = {"h2d": 0, "xyb": 1, "aq": 2, "homog": 3, "acs": 4, "coeff": 5, "tokenize": 6, "histo": 7, "ans": 8,
                "dc": 9, "assemble": 10, "d2h": 11}
 
@@ -357,7 +357,7 @@ def main():
         search = not (flags & 1) and effort >= 5
         # the HBM-bound stage the north star names: transform + quantise (18.3 B/px: 12 in, 6 out, 0.3 side data).  On
         # DCT8-only frames that is ONE kernel (k_dct8_quant_v4); on search workloads it is the strategy-binned stage
-        # (k_coeff_lists + k_coeff8<S> + k_coeffsq<N, MODE>, one launch per strategy), timed as a stage.
+        # (k_coeff_lists + k_coeff8_lanes + k_coeff8_special + k_coeffsq_all<16|32|64>, one launch per size class), timed as a stage.
         dom = "coeff"
         dom_ms = float(mean_stage[STAGE_INDEX[dom]])
         achieved = STAGE_BYTES_PER_PX[dom] * w * h / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
@@ -370,8 +370,9 @@ def main():
                                 "frac": (bpp_alg * w * h / (t_ms / 1e3) / 1e9 / peak) if t_ms > 0 else 0.0}
         acs_ms = float(mean_stage[STAGE_INDEX["acs"]])
         roof = {"bound": "hbm",
-                "kernel": ("coefficient stage of the search path: k_coeff_lists + k_coeff8<S> + k_coeffsq<N, MODE> (transform + "
-                           "quantise, one launch per strategy)") if search else "k_dct8_quant_v4 (transform + quantise)",
+                "kernel": ("coefficient stage of the search path: k_coeff_lists + k_coeff8_lanes + k_coeff8_special + "
+                           "k_coeffsq_all<16|32|64> (transform + quantise, one launch per size class)") if search
+                          else "k_dct8_quant_v4 (transform + quantise)",
                 "achieved": achieved, "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None if search else (TRAFFIC_BYTES_K7_DCT8_4K if (w, h) == (3840, 2160) else None),

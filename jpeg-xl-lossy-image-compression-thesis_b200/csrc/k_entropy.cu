@@ -152,7 +152,57 @@ __global__ void __launch_bounds__(256) k_tokenize(const uint8_t* __restrict__ ac
     // coefficient tokens: a (block, channel) has ~4.5 of them on average, so four entries are walked side by side,
     // eight lanes each (the running non-zero count comes from the group's byte of the ballot)
     __syncwarp();
-    unsigned todo = __ballot_sync(0xffffffffu, m_count > 1);
+    // Entries with more than 32 coefficient tokens (the first blocks of 16/32/64-sized transforms carry up to 4095 of them,
+    // their covered blocks none) are walked by the whole warp, one entry at a time, 32 scan positions per step: eight
+    // lanes on such an entry kept the other warps of the CTA waiting at the final barrier (57 % of the kernel's stall
+    // samples, profiles/r02k)
+    unsigned big = __ballot_sync(0xffffffffu, m_count > 33);
+    unsigned todo = __ballot_sync(0xffffffffu, m_count > 1) & ~big;
+    while (big) {
+      const int src = __ffs(big) - 1;
+      big &= big - 1;
+      const uint32_t off = __shfl_sync(0xffffffffu, m_off, src);
+      const uint32_t count = __shfl_sync(0xffffffffu, m_count, src);
+      const uint32_t misc = __shfl_sync(0xffffffffu, m_misc, src);
+      const int ee = e0 + src;
+      const int blk = ee / 3, slot = ee - blk * 3;
+      const int lx = blk & 31, ly = blk >> 5;
+      const int s = misc & 0xff, block_ctx = (misc >> 8) & 0xff;
+      int nz = (int)(misc >> 16);
+      const int cx = c_covered_x[s], cy = c_covered_y[s], n = cx * cy, size = n * 64;
+      const int log2n = 31 - __clz(n);
+      const int histo_offset = kNumBlockCtx * kNonZeroBuckets + kZeroDensityContextCount * block_ctx;
+      int prev_carry = nz > size / 16 ? 0 : 1;
+      const int last = n + (int)count - 2;
+      for (int k0 = n; k0 <= last; k0 += 32) {
+        const int k = k0 + lane;
+        int coef = 0;
+        if (k <= last) {
+          if (k < 16) {
+            coef = s_coef[warp][src][k];
+          } else {
+            const int jj = k >> 6;
+            const int jx = jj % cx, jy = jj / cx;
+            const size_t cblk = (size_t)g * kGroupBlocks + (size_t)(ly + jy) * 32 + (lx + jx);
+            coef = coeffs[(cblk * 3 + slot) * 64 + (k & 63)];
+          }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, coef != 0);
+        const int nz_here = nz - __popc(mask & ((1u << lane) - 1));
+        const int prev = lane == 0 ? prev_carry : (int)((mask >> (lane - 1)) & 1);
+        if (k <= last) {
+          const int nzl = (nz_here + n - 1) >> log2n;
+          const uint32_t ctx = (uint32_t)(histo_offset + (c_nnz_ctx[nzl] + c_freq_ctx[k >> log2n]) * 2 + prev);
+          const uint32_t v = pack_signed(coef);
+          out[off + 1 + (k - n)] = (ctx << 16) | v;
+          uint32_t tok, nb, bits;
+          hybrid_encode(v, tok, nb, bits);
+          if (tok < 2) atomicAdd(&s_hot[ctx], tok ? 0x10000u : 1u); else atomicAdd(&hist[ctx * kAcAlphabet + tok], 1u);
+        }
+        nz -= __popc(mask);
+        prev_carry = (int)(mask >> 31);
+      }
+    }
     const int gi = lane >> 3, gl = lane & 7;
     while (todo) {
       int j = -1;

@@ -27,6 +27,7 @@ struct jxlb200_ctx {
   bool use_copy_stream = true;
   int ans_warps_single = 8;           // warps per rANS CTA for a single image (4: 2.51 ms, 8: 2.45 ms, 16: 2.65 ms per 4K frame) ($JXLB200_ANS_WARPS_SINGLE)
   int ans_warps = 16;                 // warps per rANS CTA in batch mode (32 measured no faster: the chains slow down)
+  bool fork_single = true;            // a lone frame's independent stages on auxiliary streams ($JXLB200_FORK=0 switches it off)
   int ans_gpw = 2;                    // AC groups per warp of the rANS kernel in batch mode (fewer, longer-lived CTAs)
   std::vector<uint8_t> forced_acs;    // jxlb200_debug_set_strategy_map: handed to every pipeline
   int forced_bxs = 0, forced_bys = 0;
@@ -66,6 +67,7 @@ jxlb200_ctx* jxlb200_create(int device) {
   ctx->device = device;
   if (const char* env = getenv("JXLB200_PIPELINES")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->num_pipelines = v; }
   if (const char* env = getenv("JXLB200_COPY_STREAM")) ctx->use_copy_stream = atoi(env) != 0;
+  if (const char* env = getenv("JXLB200_FORK")) ctx->fork_single = atoi(env) != 0;
   if (const char* env = getenv("JXLB200_ANS_WARPS_SINGLE")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16) ctx->ans_warps_single = v; }
   if (const char* env = getenv("JXLB200_ANS_WARPS")) { const int v = atoi(env); if (v == 4 || v == 8 || v == 16) ctx->ans_warps = v; }
   if (const char* env = getenv("JXLB200_ANS_GPW")) { const int v = atoi(env); if (v >= 1 && v <= 64) ctx->ans_gpw = v; }
@@ -106,6 +108,7 @@ int jxlb200_encode_device(jxlb200_ctx* ctx, const uint8_t* d_pixels, uint32_t wi
   EncodeParams ep{params->distance, params->effort, params->proposal, params->flags};
   ctx->enc.set_ans_groups_per_warp(1);
   ctx->enc.set_ans_warps(ctx->ans_warps_single);
+  ctx->enc.set_fork(ctx->fork_single);
   if (!ctx->enc.EncodeDevice(d_pixels, (int)width, (int)height, stride, ep, stats, &e)) return fail(ctx, e);
   return 0;
 }
@@ -130,6 +133,7 @@ int jxlb200_encode(jxlb200_ctx* ctx, const jxlb200_image* image, const jxlb200_p
   ctx->enc.set_ans_groups_per_warp(1);
   ctx->enc.set_ans_warps(ctx->ans_warps_single);
   ctx->enc.set_copy_stream(nullptr);
+  ctx->enc.set_fork(ctx->fork_single);
   if (!ctx->enc.EncodeHost(image->pixels, (int)image->width, (int)image->height, image->stride, ep, stats, &e))
     return fail(ctx, e);
   if (!ctx->enc.Fetch(out, out_len, &e)) return fail(ctx, e);
@@ -169,6 +173,7 @@ int jxlb200_encode_batch(jxlb200_ctx* ctx, const jxlb200_image* images, const jx
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
     ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : ctx->ans_warps_single);
     ctx->pipe(p)->set_copy_stream(P > 1 && ctx->use_copy_stream ? ctx->copy_stream : nullptr);
+    ctx->pipe(p)->set_fork(P == 1 && ctx->fork_single);
     if (!ctx->pipe(p)->EnqueueHost(images[i].pixels, (int)images[i].width, (int)images[i].height, images[i].stride, ep, &e)) {
       rc = fail(ctx, e);
       break;
@@ -217,6 +222,7 @@ int jxlb200_encode_batch_device(jxlb200_ctx* ctx, const uint8_t* const* d_pixels
     EncodeParams ep{params[i].distance, params[i].effort, params[i].proposal, params[i].flags};
     ctx->pipe(p)->set_ans_groups_per_warp(P > 1 ? ctx->ans_gpw : 1);
     ctx->pipe(p)->set_ans_warps(P > 1 ? ctx->ans_warps : ctx->ans_warps_single);
+    ctx->pipe(p)->set_fork(P == 1 && ctx->fork_single);
     const auto tq0 = std::chrono::steady_clock::now();
     if (!ctx->pipe(p)->EnqueueDevice(d_pixels[i], (int)widths[i], (int)heights[i], strides[i], ep, &e)) { rc = fail(ctx, e); break; }
     enqueue_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq0).count();

@@ -201,10 +201,24 @@ bool Encoder::Init(int device, std::string* err) {
   return true;
 }
 
+bool Encoder::EnsureFork() {
+  if (aux_[0]) return true;
+  for (int k = 0; k < 2; ++k) {
+    if (cudaStreamCreateWithFlags(&aux_[k], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&ev_join_[k], cudaEventDisableTiming) != cudaSuccess) return false;
+  }
+  return cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming) == cudaSuccess;
+}
+
 void Encoder::Destroy() {
   if (device_ < 0) return;
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  for (int k = 0; k < 2; ++k) {
+    if (aux_[k]) { cudaStreamSynchronize(aux_[k]); cudaStreamDestroy(aux_[k]); aux_[k] = nullptr; }
+    if (ev_join_[k]) { cudaEventDestroy(ev_join_[k]); ev_join_[k] = nullptr; }
+  }
+  if (ev_fork_) { cudaEventDestroy(ev_fork_); ev_fork_ = nullptr; }
   if (ev_copy_) { cudaEventDestroy(ev_copy_); ev_copy_ = nullptr; }
   d_lut_.Release();
   for (int k = 0; k < 17; ++k) { d_weights_[k].Release(); d_dequant_[k].Release(); d_weights_t_[k].Release(); d_dequant_t_[k].Release(); }
@@ -358,6 +372,17 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   // K1: XYB
   launch_rgb8_to_xyb(d_rgb, stride, fd.xsize, fd.ysize, fd, d_lut_.p, X, Y, B, stream_);
   CUDA_OK(cudaEventRecord(ev_[2], stream_));
+  const bool fork = fork_ && EnsureFork();
+  StreamFork sf{{aux_[0], aux_[1]}, ev_fork_, {ev_join_[0], ev_join_[1]}};
+  // K4: homogeneity map (the thesis' proposals) — only the proposals read it (H8 / H9; the unpatched encoder has no use for
+  // the map); it depends on the XYB planes alone, so a lone frame computes it beside the quant field
+  const bool homog_aside = fork && p.proposal != JXLB200_PROPOSAL_NONE;
+  if (homog_aside) {
+    CUDA_OK(cudaEventRecord(ev_fork_, stream_));
+    CUDA_OK(cudaStreamWaitEvent(aux_[0], ev_fork_, 0));
+    launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, aux_[0]);
+    CUDA_OK(cudaEventRecord(ev_join_[0], aux_[0]));
+  }
   // K2: quant field
   if (p.flags & JXLB200_FLAG_UNIFORM_QF) {
     launch_fill(d_qf_.p, nblk, 0.841f / p.distance, stream_);
@@ -368,9 +393,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   }
   launch_quant_params(d_qf_.p, nblk, host_initial_quant_dc(p.distance), d_q_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[3], stream_));
-  // K4: homogeneity map (the thesis' proposals)
-  // (only the proposals read it: H8 / H9; the unpatched encoder has no use for the map)
-  if (p.proposal != JXLB200_PROPOSAL_NONE) launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
+  if (homog_aside) CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_[0], 0));
+  else if (p.proposal != JXLB200_PROPOSAL_NONE) launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
   else CUDA_OK(cudaMemsetAsync(d_homog_.p, 0, 3 * nblk * 4, stream_));
   CUDA_OK(cudaEventRecord(ev_[4], stream_));
   // K6: AC strategy search (+ the proposals' hooks); DCT8 everywhere when fixed or below effort 5
@@ -415,13 +439,41 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
     for (int o = 0; o < 17; ++o) inv_order[o] = d_inv_order_[o].p;
     launch_coeff_general(X, Y, B, d_acs_.p, fd, d_q_.p, tables, inv_order, d_cmap_.p, x_qm_mul_, b_qm_mul_,
                          p.effort >= 5 ? 1 : 0, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_nzeros_.p, d_nzcount_.p, d_lastk_.p,
-                         d_coeff_lists_.p, stream_);
+                         d_coeff_lists_.p, stream_, fork ? &sf : nullptr);
   } else {
       launch_dct8_quant_v4(X, Y, B, fd, d_q_.p, d_weights_[0].p, d_dequant_[0].p + 64, d_bias8_.p, d_lastlut8_.p, d_cmap_.p,
                            x_qm_mul_, b_qm_mul_, p.effort >= 5 ? 1 : 0, dct8_rows_, dct8_tps_, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p,
                            d_nzeros_.p, d_nzcount_.p, d_lastk_.p, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[6], stream_));
+  // K11 (moved up for a lone frame): the modular DC + AC metadata streams and LfGlobal need the coefficient stage's outputs
+  // only, so they run on an auxiliary stream beside tokenisation, clustering and the rANS chains
+  uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;
+  uint32_t* tree_bits = d_small_.p + 3;
+  auto modular_streams = [&](cudaStream_t ms) -> bool {
+    if (tree_ndc_ != fd.num_dc_groups) {
+      launch_tree_blob(fd.num_dc_groups, d_tree_words_.p, tree_bits, ms);
+      tree_ndc_ = fd.num_dc_groups;
+    }
+    CUDA_OK(cudaMemsetAsync(d_mod_hist_.p, 0, kNumModularCtx * kModAlphabet * 4, ms));
+    CUDA_OK(cudaMemsetAsync(d_mod_words_.p, 0, ((size_t)total_elems_ + 2) * 4, ms));
+    CUDA_OK(cudaMemsetAsync(d_out_info_.p + 8, 0, 32 * sizeof(unsigned long long), ms));   // acs histogram slots
+    launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p,
+                     d_out_info_.p + 8, ms);
+    launch_mod_tokens(d_dc_quant_.p, d_cmap_.p, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, fd, d_dgs_.p, fd.num_dc_groups,
+                      total_elems_, d_mod_tokens_.p, d_mod_hist_.p, ms);
+    launch_mod_codes(d_mod_hist_.p, d_q_.p, d_tree_words_.p, tree_bits, d_code_len_.p, d_code_bits_.p, d_lf_words_.p, lf_bits,
+                     ms);
+    launch_mod_write(d_mod_tokens_.p, d_code_len_.p, d_code_bits_.p, d_dgs_.p, fd.num_dc_groups, d_first_count_.p, total_elems_,
+                     d_tile_sums_.p, mod_total_bits, d_mod_words_.p, d_dg_start_.p, ms);
+    return true;
+  };
+  if (fork) {
+    CUDA_OK(cudaEventRecord(ev_fork_, stream_));
+    CUDA_OK(cudaStreamWaitEvent(aux_[0], ev_fork_, 0));
+    if (!modular_streams(aux_[0])) return false;
+    CUDA_OK(cudaEventRecord(ev_join_[0], aux_[0]));
+  }
   // K8: tokens + per-context histograms
   CUDA_OK(cudaMemsetAsync(d_hist_.p, 0, (size_t)kNumAcContexts * kAcAlphabet * 4, stream_));
   CUDA_OK(cudaMemsetAsync(d_cluster_hist_.p, 0, kMaxClusters * kAcAlphabet * 4, stream_));
@@ -433,33 +485,27 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   launch_ans_tables(d_cluster_hist_.p, d_cluster_state_.p, d_norm_.p, d_rmap_.p, d_info_.p, d_hdr_bits_.p, d_hdr_len_.p,
                     stream_);
   CUDA_OK(cudaEventRecord(ev_[8], stream_));
-  // K10: one rANS stream per AC group
   const int* d_num_clusters = reinterpret_cast<const int*>(d_cluster_state_.p + cluster_num_clusters_offset());
+  if (fork) {
+    // HfGlobal (context map + histogram headers) only needs the tables: beside the rANS chains
+    CUDA_OK(cudaEventRecord(ev_fork_, stream_));
+    CUDA_OK(cudaStreamWaitEvent(aux_[1], ev_fork_, 0));
+    launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
+                     hf_bits, aux_[1]);
+    CUDA_OK(cudaEventRecord(ev_join_[1], aux_[1]));
+  }
+  // K10: one rANS stream per AC group
   launch_ans_groups(d_tokens_.p, d_token_counts_.p, d_ctx_map_.p, d_info_.p, d_rmap_.p, d_num_clusters, d_small_.p + 4,
                     ans_groups_per_warp_, ans_warps_, d_group_arena_.p, d_group_start_.p, fd.num_groups, stream_);
   CUDA_OK(cudaEventRecord(ev_[9], stream_));
   // K11: modular DC + AC metadata streams, LfGlobal
-  uint32_t* lf_bits = d_small_.p + 0; uint32_t* mod_total_bits = d_small_.p + 1; uint32_t* hf_bits = d_small_.p + 2;
-  uint32_t* tree_bits = d_small_.p + 3;
-  if (tree_ndc_ != fd.num_dc_groups) {
-    launch_tree_blob(fd.num_dc_groups, d_tree_words_.p, tree_bits, stream_);
-    tree_ndc_ = fd.num_dc_groups;
-  }
-  CUDA_OK(cudaMemsetAsync(d_mod_hist_.p, 0, kNumModularCtx * kModAlphabet * 4, stream_));
-  CUDA_OK(cudaMemsetAsync(d_mod_words_.p, 0, ((size_t)total_elems_ + 2) * 4, stream_));
-  CUDA_OK(cudaMemsetAsync(d_out_info_.p + 8, 0, 32 * sizeof(unsigned long long), stream_));   // acs histogram slots
-  launch_mod_ranks(d_acs_.p, d_raw_qf_.p, fd, d_dgs_.p, fd.num_dc_groups, d_strat_c_.p, d_qf_c_.p, d_first_count_.p,
-                   d_out_info_.p + 8, stream_);
-  launch_mod_tokens(d_dc_quant_.p, d_cmap_.p, d_strat_c_.p, d_qf_c_.p, d_first_count_.p, fd, d_dgs_.p, fd.num_dc_groups,
-                    total_elems_, d_mod_tokens_.p, d_mod_hist_.p, stream_);
-  launch_mod_codes(d_mod_hist_.p, d_q_.p, d_tree_words_.p, tree_bits, d_code_len_.p, d_code_bits_.p, d_lf_words_.p, lf_bits,
-                   stream_);
-  launch_mod_write(d_mod_tokens_.p, d_code_len_.p, d_code_bits_.p, d_dgs_.p, fd.num_dc_groups, d_first_count_.p, total_elems_,
-                   d_tile_sums_.p, mod_total_bits, d_mod_words_.p, d_dg_start_.p, stream_);
+  if (fork) CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_[0], 0));
+  else if (!modular_streams(stream_)) return false;
   CUDA_OK(cudaEventRecord(ev_[10], stream_));
   // K12: HfGlobal, headers + TOC, concatenation
-  launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
-                   hf_bits, stream_);
+  if (fork) CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_[1], 0));
+  else launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
+                        hf_bits, stream_);
   launch_finalize(fd, x_qm_scale_, b_qm_scale_, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,
                   d_sections_.p, d_hdr_stage_.p, d_out_.p, (unsigned long long)d_out_.cap * 32, d_out_info_.p, d_q_.p,
                   d_token_counts_.p, d_num_clusters, stream_);

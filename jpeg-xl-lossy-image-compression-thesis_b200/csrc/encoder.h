@@ -51,6 +51,9 @@ class Encoder {
   // batch mode: all pipelines send their input over ONE copy stream (whole images back to back on the H2D engine
   // instead of 32 streams' copies time-sliced against each other); nullptr = copy on the encoder's own stream
   void set_copy_stream(cudaStream_t s) { copy_stream_ = s; }
+  // single-image calls: independent stages of one frame run side by side on two auxiliary streams (batch mode keeps one
+  // stream per image: the other images fill the GPU and the hardware has 32 queues)
+  void set_fork(bool on) { fork_ = on; }
 
  private:
   bool Reserve(const FrameDim& fd, std::string* err);
@@ -64,6 +67,10 @@ class Encoder {
   cudaStream_t stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copy_ = nullptr;
+  bool fork_ = false;
+  cudaStream_t aux_[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork_ = nullptr, ev_join_[2] = {nullptr, nullptr};
+  bool EnsureFork();
   cudaEvent_t ev_[16] = {};   // ev_[12] closes the optional quality stage
   FrameDim fd_{};
   EncodeParams params_{};

@@ -976,7 +976,8 @@ static void launch_coeffsq_all(const CoeffAllArgs& AA, cudaStream_t s) {
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
                           const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s) {
+                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s,
+                          const StreamFork* fork) {
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   cudaMemsetAsync(coeffs, 0, (size_t)fd.num_groups * kGroupBlocks * 192 * sizeof(int16_t), s);
   launch_coeff_lists(acs, fd, lists, s);
@@ -994,14 +995,28 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
   for (int li = 0; li < 6; ++li) AA.inv[li] = nullptr;
   // 16 / 32 / 64-sized lists: tables and inverse scan orders in 16-byte chunks, [c][chunk][lane][4] (AcsTables::wJ)
   for (int li = kList16Tall; li < kNumLists; ++li) { AA.w[li] = T.wJ[li - kList16Tall]; AA.dq[li] = T.dqJ[li - kList16Tall]; AA.inv[li] = T.invJ[li - kList16Tall]; }
+  // the five launches are independent of each other (disjoint transforms): a lone frame runs them on three streams
+  cudaStream_t s8 = s, s32 = s;
+  if (fork) {
+    cudaEventRecord(fork->fork, s);
+    cudaStreamWaitEvent(fork->aux[0], fork->fork, 0);
+    cudaStreamWaitEvent(fork->aux[1], fork->fork, 0);
+    s8 = fork->aux[1]; s32 = fork->aux[0];
+  }
   g_kernel_launches += 2;
   size_t g8 = (nblk + 15) / 16 + 4;
   if (g8 > 148 * 16) g8 = 148 * 16;
-  k_coeff8_lanes<<<(unsigned)g8, 128, 4 * kC8WarpFloats * sizeof(float), s>>>(AA);
-  k_coeff8_special<<<(unsigned)((nblk + 63) / 64 + 2 > 148 * 8 ? 148 * 8 : (nblk + 63) / 64 + 2), 64, 0, s>>>(AA);
   launch_coeffsq_all<64>(AA, s);     // (longest dependency chains first)
-  launch_coeffsq_all<32>(AA, s);
-  launch_coeffsq_all<16>(AA, s);
+  launch_coeffsq_all<32>(AA, s32);
+  launch_coeffsq_all<16>(AA, s32);
+  k_coeff8_lanes<<<(unsigned)g8, 128, 4 * kC8WarpFloats * sizeof(float), s8>>>(AA);
+  k_coeff8_special<<<(unsigned)((nblk + 63) / 64 + 2 > 148 * 8 ? 148 * 8 : (nblk + 63) / 64 + 2), 64, 0, s8>>>(AA);
+  if (fork) {
+    cudaEventRecord(fork->join[0], fork->aux[0]);
+    cudaEventRecord(fork->join[1], fork->aux[1]);
+    cudaStreamWaitEvent(s, fork->join[0], 0);
+    cudaStreamWaitEvent(s, fork->join[1], 0);
+  }
 }
 
 }  // namespace jxlb

@@ -49,10 +49,13 @@ size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-ali
 void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,
                 const FrameDim& fd, const AcsParams& P, const AcsTables& T, float* work, uint32_t* jobs, uint8_t* acs, float* est,
                 cudaStream_t s);
+// two auxiliary streams + the events that order them against the main stream (nullptr: everything on the main stream)
+struct StreamFork { cudaStream_t aux[2]; cudaEvent_t fork, join[2]; };
 void launch_coeff_general(const float* x, const float* y, const float* b, const uint8_t* acs, const FrameDim& fd,
                           const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order, const int8_t* cmap,
                           float x_qm_mul, float b_qm_mul, int adjust, int32_t* raw_qf, int16_t* coeffs, int16_t* dc_quant,
-                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s);
+                          uint8_t* nzeros, uint16_t* nzcount, uint16_t* lastk, uint32_t* lists, cudaStream_t s,
+                          const StreamFork* fork = nullptr);
 void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s);   // bins the first blocks by strategy
 size_t coeff_list_words(const FrameDim& fd);  // per-class transform lists of k_coeff / k_recon (uint32 words)
 

@@ -5,12 +5,17 @@
 //
 // The strategy map is first binned (k_coeff_lists: one list of first blocks per strategy, warp-aggregated appends), so
 // that every warp of the transform kernels runs ONE strategy's code:
-//   k_coeff8<S>     8x8 strategies, one thread per block, the block in registers (fwd8x8); the scan-order permutation
-//                   of the 64 quantised values is resolved at compile time, a channel leaves as eight 16-byte stores
-//   k_coeffsq<N, M> 16 / 32 / 64-sized strategies, one lane group of N lanes per transform (SquareXform): lane hf owns
-//                   every vertical frequency of horizontal frequency hf from the column pass to the output, the
-//                   heuristics' block sums are xor-butterflies over the lanes; X and B wait in shared memory while Y is
-//                   quantised; only non-zero coefficients are scattered into the (pre-zeroed) scan-order arena
+//   k_coeff8_lanes     DCT, DCT4X4, DCT4X8, DCT8X4: eight lanes per block, four blocks per warp (the geometry of
+//                      k_acs_evalsq<8>); a block's three channels stay in 24 registers per lane, a channel leaves as
+//                      128 contiguous bytes in scan order
+//   k_coeff8_special   IDENTITY, DCT2X2 (rare): one thread per block, the block in registers (fwd8x8)
+//   k_coeffsq_all<N>   16 / 32 / 64-sized strategies, one lane group of N lanes per transform: a channel's tile is the
+//                      landing zone of its pixels (coalesced cp.async), the transposition buffer and then the lane-ordered
+//                      home of the coefficients (lane hf owns every vertical frequency of horizontal frequency hf); the
+//                      heuristics' block sums are per-lane sequential sums + xor-butterflies over the lanes; quant
+//                      adjustment and quantisation are rolled loops over 16-byte chunks of the lane's row; only non-zero
+//                      coefficients are scattered into the (pre-zeroed) scan-order arena
+// A lone frame runs the five launches on three streams (StreamFork); in batch mode they share the image's stream.
 #include "transforms.cuh"
 #include "kernels.h"
 

@@ -373,12 +373,19 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
     }
     if (lane == 0) { s_wkey[warp] = best_key; s_wctx[warp] = best_ctx; }
     __syncthreads();
-    if (t == 0) {
-      long long k = s_wkey[0]; int c = s_wctx[0];
-      for (int w = 1; w < kClusterThreads / 32; ++w) if (better(s_wkey[w], s_wctx[w], k, c)) { k = s_wkey[w]; c = s_wctx[w]; }
-      for (int r = 0; r < kClusterCtas; ++r) {
-        long long* rk = cluster.map_shared_rank(&s_cand_key[parity][0], r);
-        int* rc = cluster.map_shared_rank(&s_cand_ctx[parity][0], r);
+    if (warp == 0) {
+      // the CTA's best of its 16 warps (a butterfly over lanes 0..15), then lane r tells rank r
+      long long k = lane < kClusterThreads / 32 ? s_wkey[lane] : -1;
+      int c = lane < kClusterThreads / 32 ? s_wctx[lane] : 0x7fffffff;
+#pragma unroll
+      for (int d = 8; d >= 1; d >>= 1) {
+        const long long ok = __shfl_xor_sync(0xffffffffu, k, d);
+        const int oc = __shfl_xor_sync(0xffffffffu, c, d);
+        if (better(ok, oc, k, c)) { k = ok; c = oc; }
+      }
+      if (lane < kClusterCtas) {
+        long long* rk = cluster.map_shared_rank(&s_cand_key[parity][0], lane);
+        int* rc = cluster.map_shared_rank(&s_cand_ctx[parity][0], lane);
         rk[rank] = k; rc[rank] = c;
       }
     }
@@ -403,26 +410,42 @@ __global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kClusterT
     best_key = -1; best_ctx = 0x7fffffff;
 #pragma unroll
     for (int sl = 0; sl < kCtxSlots; ++sl) {
+      // four contexts per trip: their partial sums and the four 64-bit butterflies are independent, so the shuffle
+      // latencies of one overlap the arithmetic of the others (integer sums: any order gives the same value)
       unsigned mask = ne_mask[sl];
+      const uint32_t b0 = s_hb[lane], b1 = s_hb[lane + 32];
+      const long long xb0 = s_xb[lane], xb1 = s_xb[lane + 32];
       while (mask) {
-        const int i = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int c = gwarp + (sl * 32 + i) * kClusterWarps;
-        const int r = cache_base[sl] + __popc(ne_mask[sl] & ((1u << i) - 1));
-        const uint32_t* h = r < kCacheCap ? my_cache + r * kAcAlphabet : hist + (size_t)c * kAcAlphabet;
-        long long acc = 0;
+        int idx[4];
+        long long acc[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int s = lane + 32 * half;
-          const uint32_t a = h[s], b = s_hb[s];
-          if (a && b) acc += xlogx(a + b, s_lut) - xlogx(a, s_lut) - s_xb[s];
+        for (int u = 0; u < 4; ++u) {
+          idx[u] = mask ? __ffs(mask) - 1 : -1;
+          if (mask) mask &= mask - 1;
+          acc[u] = 0;
+          if (idx[u] >= 0) {
+            const int c = gwarp + (sl * 32 + idx[u]) * kClusterWarps;
+            const int r = cache_base[sl] + __popc(ne_mask[sl] & ((1u << idx[u]) - 1));
+            const uint32_t* h = r < kCacheCap ? my_cache + r * kAcAlphabet : hist + (size_t)c * kAcAlphabet;
+            const uint32_t a0 = h[lane], a1 = h[lane + 32];
+            if (a0 && b0) acc[u] += xlogx(a0 + b0, s_lut) - xlogx(a0, s_lut) - xb0;
+            if (a1 && b1) acc[u] += xlogx(a1 + b1, s_lut) - xlogx(a1, s_lut) - xb1;
+          }
         }
-        acc = warp_sum_ll(acc);
-        if (lane == i) {
-          const uint32_t ta = my_total[sl];
-          long long d = xlogx(ta + tb, s_lut) - xlogx(ta, s_lut) - xtb - acc;
-          if (c == seed) d = 0;
-          if (d < my_dist[sl]) { my_dist[sl] = d; my_assign[sl] = k; }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], d);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (idx[u] >= 0 && lane == idx[u]) {
+            const int c = gwarp + (sl * 32 + idx[u]) * kClusterWarps;
+            const uint32_t ta = my_total[sl];
+            long long d = xlogx(ta + tb, s_lut) - xlogx(ta, s_lut) - xtb - acc[u];
+            if (c == seed) d = 0;
+            if (d < my_dist[sl]) { my_dist[sl] = d; my_assign[sl] = k; }
+          }
         }
       }
       const int c = gwarp + (sl * 32 + lane) * kClusterWarps;

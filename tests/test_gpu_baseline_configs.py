@@ -129,3 +129,67 @@ def test_forced_strategy_map_parity(pkg, oracle, encoder):
         encoder.set_strategy_map(bad)
     with pytest.raises(pkg.EncodeError):
         encoder.encode(pkg.synth_image(64, 64, 1), 1.0, 7, 0, pkg.FLAG_FORCED_ACS)   # map of another frame size
+
+
+def test_six_worker_threads_with_their_own_contexts(pkg, oracle):
+    """The reference's threading contract (benchmark.rs:97-103, config.rs:22): up to six OS threads call the encoder at the
+    same time, each with its own context.  Every thread's codestreams equal the oracle's."""
+    import threading
+    jobs = [(264 + 8 * k, 200 - 8 * k, 40 + k, (0.5, 1.0, 2.0)[k % 3], k % 4) for k in range(6)]
+    want = {}
+    for (w, h, seed, dist, prop) in jobs:
+        want[(w, h, seed)] = oracle.encode(pkg.synth_image(w, h, seed), dist, 7, prop, 0).dump("codestream").tobytes()
+    errors = []
+
+    def worker(job):
+        w, h, seed, dist, prop = job
+        try:
+            img = pkg.synth_image(w, h, seed)
+            with pkg.Encoder(0) as enc:
+                for _ in range(4):
+                    data, st = enc.encode(img, dist, 7, prop, 0)
+                    if data != want[(w, h, seed)]:
+                        errors.append(("mismatch", job))
+        except Exception as e:  # noqa: BLE001
+            errors.append((repr(e), job))
+
+    threads = [threading.Thread(target=worker, args=(j,)) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_forked_single_frame_equals_the_single_stream_one(pkg, oracle, monkeypatch):
+    """A lone frame runs independent stages on auxiliary streams ($JXLB200_FORK, default on); with the fork switched off
+    the same bytes and the same intermediates come out, and both equal the oracle."""
+    img = pkg.synth_image(520, 392, 77)
+    ora = oracle.encode(img, 1.0, 7, 3, 0)
+    out = {}
+    for fork in ("1", "0"):
+        monkeypatch.setenv("JXLB200_FORK", fork)
+        with pkg.Encoder(0) as enc:
+            for _ in range(3):
+                data, st = enc.encode(img, 1.0, 7, 3, pkg.FLAG_QUALITY)
+            out[fork] = (data, st.sse, enc.dump("homog").tobytes(), enc.dump("dc_quant").tobytes(), enc.dump("tokens").tobytes())
+    assert out["1"] == out["0"]
+    assert np.array_equal(np.frombuffer(out["1"][0], dtype=np.uint8), ora.dump("codestream"))
+    assert out["1"][1] == [int(v) for v in ora.sse(img)]
+
+
+def test_forced_strategy_map_in_batch_mode(pkg, oracle):
+    """jxlb200_debug_set_strategy_map reaches every pipeline of the context: a batch with JXLB200_FLAG_FORCED_ACS gives the
+    single encode's bytes on every pipeline."""
+    from test_oracle_entropy import every_strategy_map
+    w, h = 264, 200
+    d = pkg.frame_dims(w, h)
+    acs = every_strategy_map(d["bys"], d["bxs"], seed=3)
+    imgs = [pkg.synth_image(w, h, 90 + i) for i in range(6)]
+    with pkg.Encoder(0) as enc:
+        enc.set_strategy_map(acs)
+        enc.set_pipelines(4)
+        datas, _ = enc.encode_batch(imgs, 1.0, 7, 0, pkg.FLAG_FORCED_ACS)
+        for img, data in zip(imgs, datas):
+            ora = oracle.encode_forced(img, acs, 1.0, 7, 0, 0)
+            assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream"))

@@ -60,6 +60,7 @@ pub const JXLB200_FLAG_FIXED_DCT8: u32 = 1;
 pub const JXLB200_FLAG_UNIFORM_QF: u32 = 2;
 pub const JXLB200_FLAG_QUALITY: u32 = 4;
 pub const JXLB200_FLAG_FORCED_ACS: u32 = 8;
+pub const JXLB200_FLAG_GABORISH: u32 = 16;
 
 extern "C" {
     pub fn jxlb200_abi_version() -> c_int;

@@ -48,6 +48,9 @@ enum {
 #define JXLB200_FLAG_UNIFORM_QF 2u /* skip the adaptive quant field: qf = 0.841/distance everywhere   */
 #define JXLB200_FLAG_FORCED_ACS 8u /* use the map of jxlb200_debug_set_strategy_map instead of the search (jxlb200_encode only)  */
 #define JXLB200_FLAG_QUALITY 4u    /* also reconstruct the coded frame on the device and fill stats.sse / stats.psnr  */
+#define JXLB200_FLAG_GABORISH 16u  /* Gaborish loop filter: signal the decoder's default 3x3 blur and sharpen the XYB planes with its
+                                      5x5 least-squares inverse before the search (libjxl's default is on, with its own tuned
+                                      kernel; off here unless asked for: SURVEY 8a row U3)                              */
 
 /* Input image: 8-bit sRGB, interleaved RGB, row-major (what the harness hands to cjxl
  * as a PNG; image_reader.rs ColorType::Rgb8).  `stride` is bytes per row (>= 3*width). */

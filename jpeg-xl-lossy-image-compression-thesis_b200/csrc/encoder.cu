@@ -225,6 +225,7 @@ void Encoder::Destroy() {
   for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
   for (int k = 0; k < 6; ++k) { d_weights_c_[k].Release(); d_dequant_c_[k].Release(); }
   for (int k = 0; k < 11; ++k) { d_weights_j_[k].Release(); d_dequant_j_[k].Release(); d_inv_j_[k].Release(); }
+  d_xyb_gab_.Release();
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 17; ++o) d_inv_order_[o].Release();
@@ -376,7 +377,8 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   StreamFork sf{{aux_[0], aux_[1]}, ev_fork_, {ev_join_[0], ev_join_[1]}};
   // K4: homogeneity map (the thesis' proposals) — only the proposals read it (H8 / H9; the unpatched encoder has no use for
   // the map); it depends on the XYB planes alone, so a lone frame computes it beside the quant field
-  const bool homog_aside = fork && p.proposal != JXLB200_PROPOSAL_NONE;
+  const bool gab = (p.flags & JXLB200_FLAG_GABORISH) != 0;
+  const bool homog_aside = fork && !gab && p.proposal != JXLB200_PROPOSAL_NONE;   // (with Gaborish the map reads the sharpened planes)
   if (homog_aside) {
     CUDA_OK(cudaEventRecord(ev_fork_, stream_));
     CUDA_OK(cudaStreamWaitEvent(aux_[0], ev_fork_, 0));
@@ -393,6 +395,14 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   }
   launch_quant_params(d_qf_.p, nblk, host_initial_quant_dc(p.distance), d_q_.p, stream_);
   CUDA_OK(cudaEventRecord(ev_[3], stream_));
+  // Gaborish (opt-in): the quant field relies on the pre-sharpening values; the homogeneity map, the search and the
+  // coefficients see the sharpened planes (oracle EncodeFrame)
+  if (gab) {
+    if (!d_xyb_gab_.Reserve(3 * plane)) { *err = "device allocation failed"; return false; }
+    launch_gab_inverse(d_xyb_.p, d_xyb_gab_.p, fd, stream_);
+    X = d_xyb_gab_.p; Y = X + plane; B = Y + plane;
+  }
+  xyb_cur_ = X;
   if (homog_aside) CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_[0], 0));
   else if (p.proposal != JXLB200_PROPOSAL_NONE) launch_homogeneity(X, Y, B, fd, p.distance, d_homog_.p, stream_);
   else CUDA_OK(cudaMemsetAsync(d_homog_.p, 0, 3 * nblk * 4, stream_));
@@ -506,7 +516,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   if (fork) CUDA_OK(cudaStreamWaitEvent(stream_, ev_join_[1], 0));
   else launch_hf_global(d_ctx_map_.p, d_num_clusters, d_hdr_bits_.p, d_hdr_len_.p, fd.num_groups, d_cm_back_.p, d_hf_words_.p,
                         hf_bits, stream_);
-  launch_finalize(fd, x_qm_scale_, b_qm_scale_, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,
+  launch_finalize(fd, x_qm_scale_, b_qm_scale_, gab ? 1 : 0, lf_bits, d_dg_start_.p, mod_total_bits, hf_bits, d_group_start_.p,
                   d_sections_.p, d_hdr_stage_.p, d_out_.p, (unsigned long long)d_out_.cap * 32, d_out_info_.p, d_q_.p,
                   d_token_counts_.p, d_num_clusters, stream_);
   launch_assemble(d_sections_.p, 2 + fd.num_dc_groups + fd.num_groups, d_lf_words_.p, d_mod_words_.p, d_hf_words_.p,
@@ -520,7 +530,7 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
     if (!search) launch_coeff_lists(d_acs_.p, fd, d_coeff_lists_.p, stream_);   // (the search path binned the map already)
     launch_recon_sse(fd, d_q_.p, tables, inv_order, d_cmap_.p, 1.0f / powf(1.25f, (float)(x_qm_scale_ - 2)),
                      1.0f / powf(1.25f, (float)(b_qm_scale_ - 2)), d_acs_.p, d_raw_qf_.p, d_coeffs_.p, d_dc_quant_.p, d_rgb, stride,
-                     d_recon_tab_.p, d_coeff_lists_.p, d_recon_xyb_.p, d_out_info_.p + 36, stream_);
+                     d_recon_tab_.p, d_coeff_lists_.p, d_recon_xyb_.p, d_out_info_.p + 36, gab ? 1 : 0, stream_);
   }
   CUDA_OK(cudaEventRecord(ev_[12], stream_));
   CUDA_OK(cudaMemcpyAsync(h_out_info_, d_out_info_.p, 40 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
@@ -638,7 +648,7 @@ int64_t Encoder::Dump(int stage, void* dst, size_t cap, std::string* err) {
   const void* src = nullptr;
   size_t bytes = 0;
   switch (stage) {
-    case JXLB200_STAGE_XYB: src = d_xyb_.p; bytes = 3 * plane * 4; break;
+    case JXLB200_STAGE_XYB: src = xyb_cur_ ? xyb_cur_ : d_xyb_.p; bytes = 3 * plane * 4; break;
     case JXLB200_STAGE_QF_FLOAT: src = d_qf_.p; bytes = nblk * 4; break;
     case JXLB200_STAGE_MASK1X1: src = d_mask1x1_.p; bytes = plane * 4; break;
     case JXLB200_STAGE_MASK: src = d_mask_.p; bytes = nblk * 4; break;

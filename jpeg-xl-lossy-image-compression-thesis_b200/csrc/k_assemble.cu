@@ -118,7 +118,7 @@ __device__ void write_size_u32(BitWriterDev& w, uint32_t v) {
   else { w.write(2, 3); w.write(30, m); }
 }
 
-__global__ void __launch_bounds__(256) k_finalize(FrameDim fd, int x_qm_scale, int b_qm_scale, const uint32_t* __restrict__ lf_bits,
+__global__ void __launch_bounds__(256) k_finalize(FrameDim fd, int x_qm_scale, int b_qm_scale, int gab, const uint32_t* __restrict__ lf_bits,
                                                  const uint32_t* __restrict__ dg_start_bit, const uint32_t* __restrict__ mod_total_bits,
                                                  const uint32_t* __restrict__ hf_bits, const unsigned long long* __restrict__ group_start_bit,
                                                  Section* __restrict__ sections, uint32_t* __restrict__ hdr_stage,
@@ -180,7 +180,9 @@ __global__ void __launch_bounds__(256) k_finalize(FrameDim fd, int x_qm_scale, i
   w.write(3, (uint32_t)x_qm_scale); w.write(3, (uint32_t)b_qm_scale);
   w.write(2, 0); w.write(1, 0); w.write(2, 0);    // one pass, no crop, blend replace
   w.write(1, 1); w.write(2, 0);                   // is_last, no name
-  w.write(1, 0); w.write(1, 0); w.write(2, 0); w.write(2, 0);  // loop filter: gab off, epf 0, no extensions
+  w.write(1, 0); w.write(1, gab ? 1u : 0u);       // loop filter: not all_default, gab
+  if (gab) w.write(1, 0);                         //   default Gaborish weights
+  w.write(2, 0); w.write(2, 0);                   //   epf 0, no extensions
   w.write(2, 0);                                  // no frame-header extensions
   w.write(1, 0);                                  // TOC not permuted
   if (w.bits() & 7) w.write(8 - (int)(w.bits() & 7), 0);
@@ -254,7 +256,7 @@ void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32
   k_hf_global<<<1, 256, 0, s>>>(cmap, num_clusters, hdr_bits, hdr_len, num_groups, cm_back, hf_words, hf_bits);
 }
 
-void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
+void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, int gab, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
                      const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
                      Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
                      unsigned long long* out_info, const QuantDev* qd, const uint32_t* token_counts, const int* num_clusters,
@@ -262,7 +264,7 @@ void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const u
   ++g_kernel_launches;
   const size_t smem = (size_t)2 * (2 + fd.num_dc_groups + fd.num_groups) * sizeof(unsigned long long);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_finalize<<<1, 256, smem, s>>>(fd, x_qm_scale, b_qm_scale, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
+  k_finalize<<<1, 256, smem, s>>>(fd, x_qm_scale, b_qm_scale, gab, lf_bits, dg_start_bit, mod_total_bits, hf_bits, group_start_bit,
                              sections, hdr_stage, out_words, out_capacity_bits, out_info, qd, token_counts, num_clusters);
 }
 

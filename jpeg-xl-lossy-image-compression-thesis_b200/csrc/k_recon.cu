@@ -246,8 +246,24 @@ __device__ __forceinline__ int srgb_code(const float* tab, int k, float mix0, fl
   return lo;
 }
 
+// the decoder's default Gaborish blur of pixel (x, y) of one plane, mirrored at the image borders (oracle GaborishBlurAt)
+__device__ __forceinline__ int recon_mirror(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+  return i;
+}
+__device__ __forceinline__ float gab_blur_at(const float* __restrict__ pl, const FrameDim& fd, int x, int y) {
+  const float w1 = 0.115169525f, w2 = 0.061248592f;
+  const float norm = 1.0f / (1.0f + 4.0f * w1 + 4.0f * w2);
+  const float wc = norm, we = w1 * norm, wd = w2 * norm;
+  const int xm = recon_mirror(x - 1, fd.xsize), xp = recon_mirror(x + 1, fd.xsize);
+  const size_t r0 = (size_t)recon_mirror(y - 1, fd.ysize) * fd.pitch, r1 = (size_t)y * fd.pitch, r2 = (size_t)recon_mirror(y + 1, fd.ysize) * fd.pitch;
+  const float s1 = (pl[r1 + xm] + pl[r1 + xp]) + (pl[r0 + x] + pl[r2 + x]);
+  const float s2 = (pl[r0 + xm] + pl[r0 + xp]) + (pl[r2 + xm] + pl[r2 + xp]);
+  return __fmaf_rn(wd, s2, __fmaf_rn(we, s1, wc * pl[r1 + x]));
+}
+
 __global__ void __launch_bounds__(256) k_recon_sse(const float* __restrict__ xyb, FrameDim fd, const uint8_t* __restrict__ rgb, size_t stride,
-                                                   const float* __restrict__ tables, unsigned long long* __restrict__ sse3) {
+                                                   const float* __restrict__ tables, unsigned long long* __restrict__ sse3, int gab) {
   __shared__ float tab[9 + 255];
   for (int i = threadIdx.x; i < 9 + 255; i += 256) tab[i] = tables[i];
   __syncthreads();
@@ -257,7 +273,8 @@ __global__ void __launch_bounds__(256) k_recon_sse(const float* __restrict__ xyb
   const int gy = blockIdx.y;
   for (int gx = blockIdx.x * 256 + threadIdx.x; gx < fd.xsize; gx += gridDim.x * 256) {
     const size_t p = (size_t)gy * fd.pitch + gx;
-    const float X = xyb[p], Y = xyb[plane + p], Bv = xyb[2 * plane + p];
+    float X = xyb[p], Y = xyb[plane + p], Bv = xyb[2 * plane + p];
+    if (gab) { X = gab_blur_at(xyb, fd, gx, gy); Y = gab_blur_at(xyb + plane, fd, gx, gy); Bv = gab_blur_at(xyb + 2 * plane, fd, gx, gy); }
     const float l = (Y + X) - kNegBiasCbrt, m = (Y - X) - kNegBiasCbrt, s = Bv - kNegBiasCbrt;
     const float mix0 = (l * l) * l - kBias, mix1 = (m * m) * m - kBias, mix2 = (s * s) * s - kBias;
     const uint8_t* o = rgb + (size_t)gy * stride + 3 * (size_t)gx;
@@ -301,7 +318,7 @@ void launch_reconsq(ReconArgs A, int list_id, const float* dq, const uint16_t* i
 void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order,
                       const int8_t* cmap, float inv_qm_x, float inv_qm_b, const uint8_t* acs, const int32_t* raw_qf,
                       const int16_t* coeffs, const int16_t* dc_quant, const uint8_t* rgb, size_t stride, const float* tables,
-                      const uint32_t* lists, float* scratch_xyb, unsigned long long* sse3, cudaStream_t s) {
+                      const uint32_t* lists, float* scratch_xyb, unsigned long long* sse3, int gab, cudaStream_t s) {
   (void)acs;
   const size_t nblk = (size_t)fd.bxs * fd.bys;
   ReconArgs A;
@@ -325,7 +342,7 @@ void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T
   launch_reconsq<32, kModeTall4>(A, kList32Tall4, T.dq[7], inv_order[5], lists, nblk, s);
   launch_reconsq<32, kModeWide4>(A, kList32Wide4, T.dqT[7], inv_order[16], lists, nblk, s);
   ++g_kernel_launches;
-  k_recon_sse<<<dim3((fd.xsize + 255) / 256, fd.ysize), 256, 0, s>>>(scratch_xyb, fd, rgb, stride, tables, sse3);
+  k_recon_sse<<<dim3((fd.xsize + 255) / 256, fd.ysize), 256, 0, s>>>(scratch_xyb, fd, rgb, stride, tables, sse3, gab);
 }
 
 }  // namespace jxlb

@@ -59,11 +59,14 @@ void launch_coeff_general(const float* x, const float* y, const float* b, const 
 void launch_coeff_lists(const uint8_t* acs, const FrameDim& fd, uint32_t* lists, cudaStream_t s);   // bins the first blocks by strategy
 size_t coeff_list_words(const FrameDim& fd);  // per-class transform lists of k_coeff / k_recon (uint32 words)
 
+// Gaborish, encoder side (k_gab.cu; opt-in JXLB200_FLAG_GABORISH): 5x5 sharpening of the padded XYB planes, src -> dst
+void launch_gab_inverse(const float* src, float* dst, const FrameDim& fd, cudaStream_t s);
+
 // K13 (k_recon.cu): per-channel sum of squared errors of the coded frame's reconstruction against the input pixels
 void launch_recon_sse(const FrameDim& fd, const QuantDev* qd, const AcsTables& T, const uint16_t* const* inv_order,
                       const int8_t* cmap, float inv_qm_x, float inv_qm_b, const uint8_t* acs, const int32_t* raw_qf,
                       const int16_t* coeffs, const int16_t* dc_quant, const uint8_t* rgb, size_t stride, const float* tables,
-                      const uint32_t* lists, float* scratch_xyb, unsigned long long* sse3, cudaStream_t s);
+                      const uint32_t* lists, float* scratch_xyb, unsigned long long* sse3, int gab, cudaStream_t s);
 
 // ---- entropy stage -------------------------------------------------------------------------
 // one 2048x2048 DC group: rectangle in blocks, its 64x64-tile rectangle, first element / first block slot
@@ -99,7 +102,7 @@ void launch_mod_write(const uint32_t* tokens, const uint8_t* code_len, const uin
 // K12 (k_assemble.cu)
 void launch_hf_global(const uint8_t* cmap, const int* num_clusters, const uint32_t* hdr_bits, const uint32_t* hdr_len,
                       int num_groups, uint32_t* cm_back, uint32_t* hf_words, uint32_t* hf_bits, cudaStream_t s);
-void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
+void launch_finalize(const FrameDim& fd, int x_qm_scale, int b_qm_scale, int gab, const uint32_t* lf_bits, const uint32_t* dg_start_bit,
                      const uint32_t* mod_total_bits, const uint32_t* hf_bits, const unsigned long long* group_start_bit,
                      Section* sections, uint32_t* hdr_stage, uint32_t* out_words, unsigned long long out_capacity_bits,
                      unsigned long long* out_info, const QuantDev* qd, const uint32_t* token_counts, const int* num_clusters,

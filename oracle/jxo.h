@@ -87,6 +87,9 @@ float CbrtPos(float x);
 // rgb: h*w*3 interleaved, row stride in bytes.  Output: 3 planes of ys_pad*pitch
 // floats (edge-replicated to the padded size, pitch padding zero-filled).
 void RgbToXyb(const uint8_t* rgb, int w, int h, size_t stride, const FrameDim& fd, float* x, float* y, float* b);
+// Gaborish (jxo_xyb.cc): the encoder's sharpening of the padded XYB planes, the decoder's blur of one pixel
+void GaborishInverse(const FrameDim& fd, float* planes[3]);
+float GaborishBlurAt(const float* plane, int pitch, int xsize, int ysize, int x, int y);
 
 // ---------------------------------------------------------------- stage: transforms (U5)
 // 1-D scaled DCT-II / its inverse over `n` floats with stride; n in {2,4,8,16,32,64}

@@ -47,7 +47,8 @@ void WriteFrameHeader(const Frame& f, BitWriter* w) {
   w->Write(1, 1);      // is_last
   w->Write(2, 0);      // name length 0
   w->Write(1, 0);      // loop_filter.all_default = false
-  w->Write(1, 0);      //   gab = false
+  w->Write(1, f.gab ? 1 : 0);      //   gab
+  if (f.gab) w->Write(1, 0);       //   gab_custom = false (default weights)
   w->Write(2, 0);      //   epf_iters = 0
   w->Write(2, 0);      //   loop_filter extensions = 0
   w->Write(2, 0);      // frame header extensions = 0

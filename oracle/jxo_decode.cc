@@ -344,7 +344,8 @@ bool DecodeCodestream(const uint8_t* data, size_t size, Frame* f) {
   if (!r.Read(1)) return fail("not last frame");
   if (r.Read(2) != 0) return fail("name");
   if (r.Read(1)) return fail("default loop filter");
-  if (r.Read(1)) return fail("gaborish");
+  f->gab = r.Read(1) != 0;
+  if (f->gab && r.Read(1)) return fail("custom gaborish weights");
   if (r.Read(2) != 0) return fail("epf");
   if (r.ReadU64() != 0) return fail("lf extensions");
   if (r.ReadU64() != 0) return fail("extensions");

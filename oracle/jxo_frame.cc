@@ -123,6 +123,13 @@ bool EncodeFrame(const uint8_t* rgb, int w, int h, size_t stride, const Params& 
   }
   ComputeGlobalScale(f->qf_float.data(), nblk, InitialQuantDC(p.distance), &f->q);
 
+  // Gaborish (opt-in): the quant field above relies on the pre-sharpening values (libjxl enc_heuristics.cc order
+  // [UPSTREAM]); the homogeneity map, the search and the coefficients see the sharpened planes
+  f->gab = (p.flags & kFlagGaborish) != 0;
+  if (f->gab) {
+    float* planes[3] = {f->xyb[0].data(), f->xyb[1].data(), f->xyb[2].data()};
+    GaborishInverse(fd, planes);
+  }
   HomogeneityMap(f);
 
   f->cmap.assign((size_t)2 * fd.txs * fd.tys, 0);

@@ -12,7 +12,7 @@ struct Params {
   uint32_t proposal = 0;  // 0 none, 1 partitioning, 2 factored-entropy, 3 combined
   uint32_t flags = 0;     // bit0: fixed DCT8 strategy; bit1: uniform quant field
 };
-enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u, kFlagForcedAcs = 8u };
+enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u, kFlagForcedAcs = 8u, kFlagGaborish = 16u };
 
 // stage ids — identical to JXLB200_STAGE_* in include/jxlb200.h
 enum Stage : int {
@@ -29,6 +29,7 @@ struct Frame {
   FrameDim fd;
   Params params;
   QuantState q;
+  bool gab = false;                   // loop filter: Gaborish with the default weights (kFlagGaborish / decoded header)
   std::vector<float> xyb[3];          // ys_pad * pitch
   std::vector<float> qf_float;        // bys * bxs
   std::vector<float> mask;            // bys * bxs

@@ -131,7 +131,9 @@ bool ReconstructRgb(const Frame& f, uint8_t* rgb) {
   SrgbBoundaries(bnd);
   for (int y = 0; y < fd.ysize; ++y) for (int x = 0; x < fd.xsize; ++x) {
     const size_t p = (size_t)y * fd.pitch + x;
-    XybToSrgb8(xyb[0][p], xyb[1][p], xyb[2][p], inv, bnd, &rgb[((size_t)y * fd.xsize + x) * 3]);
+    float v[3] = {xyb[0][p], xyb[1][p], xyb[2][p]};
+    if (f.gab) for (int c = 0; c < 3; ++c) v[c] = GaborishBlurAt(xyb[c].data(), fd.pitch, fd.xsize, fd.ysize, x, y);
+    XybToSrgb8(v[0], v[1], v[2], inv, bnd, &rgb[((size_t)y * fd.xsize + x) * 3]);
   }
   return true;
 }

@@ -80,4 +80,54 @@ void RgbToXyb(const uint8_t* rgb, int w, int h, size_t stride, const FrameDim& f
   }
 }
 
+// ---- Gaborish (row U3, opt-in: kFlagGaborish) ------------------------------------------------------------------------
+// Decoder side (ISO/IEC 18181-1 loop filter, default weights): every channel is convolved with the 3x3 kernel
+// [w2 w1 w2; w1 1 w1; w2 w1 w2] / (1 + 4 w1 + 4 w2), w1 = 0.115169525, w2 = 0.061248592 [UPSTREAM, recalled], mirrored at the
+// image borders.  Encoder side: libjxl sharpens the XYB planes with a hand-tuned 5x5 kernel before the search
+// (enc_gaborish.cc, constants not available offline); any kernel is a legal encoder choice, and this one is the
+// least-squares inverse of the decoder's kernel (tools/gen_gab_inverse.py), six weights by symmetry class.
+// Both are defined with a fixed association so that the CUDA kernels reproduce them bit for bit.
+static inline int Mirror(int i, int n) {
+  while (i < 0 || i >= n) i = i < 0 ? -i - 1 : 2 * n - 1 - i;
+  return i;
+}
+
+static const float kGabInv[6] = {1.758123398e+00f, -1.690203995e-01f, -7.491233945e-02f,
+                                 2.443357371e-02f, 1.462947764e-02f, 7.093405002e-04f};
+
+// in place on the xs_pad x ys_pad region of the three planes (the pitch padding beyond xs_pad stays zero)
+void GaborishInverse(const FrameDim& fd, float* planes[3]) {
+  const int W = fd.xs_pad, H = fd.ys_pad;
+  std::vector<float> src((size_t)W * H);
+  for (int c = 0; c < 3; ++c) {
+    float* pl = planes[c];
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) src[(size_t)y * W + x] = pl[(size_t)y * fd.pitch + x];
+    auto at = [&](int x, int y) { return src[(size_t)Mirror(y, H) * W + Mirror(x, W)]; };
+    for (int y = 0; y < H; ++y) for (int x = 0; x < W; ++x) {
+      const float s0 = at(x, y);
+      const float s1 = (at(x - 1, y) + at(x + 1, y)) + (at(x, y - 1) + at(x, y + 1));
+      const float s2 = (at(x - 1, y - 1) + at(x + 1, y - 1)) + (at(x - 1, y + 1) + at(x + 1, y + 1));
+      const float s3 = (at(x - 2, y) + at(x + 2, y)) + (at(x, y - 2) + at(x, y + 2));
+      const float s4 = ((at(x - 2, y - 1) + at(x + 2, y - 1)) + (at(x - 2, y + 1) + at(x + 2, y + 1))) +
+                       ((at(x - 1, y - 2) + at(x + 1, y - 2)) + (at(x - 1, y + 2) + at(x + 1, y + 2)));
+      const float s5 = (at(x - 2, y - 2) + at(x + 2, y - 2)) + (at(x - 2, y + 2) + at(x + 2, y + 2));
+      float v = kGabInv[0] * s0;
+      v = fmaf(kGabInv[1], s1, v); v = fmaf(kGabInv[2], s2, v); v = fmaf(kGabInv[3], s3, v);
+      v = fmaf(kGabInv[4], s4, v); v = fmaf(kGabInv[5], s5, v);
+      pl[(size_t)y * fd.pitch + x] = v;
+    }
+  }
+}
+
+// the decoder's blur of pixel (x, y) of one plane, mirrored at the borders of the xsize x ysize image
+float GaborishBlurAt(const float* plane, int pitch, int xsize, int ysize, int x, int y) {
+  const float w1 = 0.115169525f, w2 = 0.061248592f;
+  const float norm = 1.0f / (1.0f + 4.0f * w1 + 4.0f * w2);
+  const float wc = norm, we = w1 * norm, wd = w2 * norm;
+  auto at = [&](int xx, int yy) { return plane[(size_t)Mirror(yy, ysize) * pitch + Mirror(xx, xsize)]; };
+  const float s1 = (at(x - 1, y) + at(x + 1, y)) + (at(x, y - 1) + at(x, y + 1));
+  const float s2 = (at(x - 1, y - 1) + at(x + 1, y - 1)) + (at(x - 1, y + 1) + at(x + 1, y + 1));
+  return fmaf(wd, s2, fmaf(we, s1, wc * at(x, y)));
+}
+
 }  // namespace jxo

@@ -193,3 +193,25 @@ def test_forced_strategy_map_in_batch_mode(pkg, oracle):
         for img, data in zip(imgs, datas):
             ora = oracle.encode_forced(img, acs, 1.0, 7, 0, 0)
             assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream"))
+
+
+@pytest.mark.parametrize("w,h,distance,proposal", [(520, 392, 1.0, 3), (264, 200, 3.0, 0), (100, 60, 0.5, 1), (1000, 700, 2.0, 2)])
+def test_gaborish_parity(pkg, oracle, encoder, w, h, distance, proposal):
+    """Row U3 (opt-in JXLB200_FLAG_GABORISH): the sharpened planes, everything computed from them, the codestream (loop
+    filter bit set) and the quality statistics (reconstruction through the decoder's blur) equal the oracle's; the
+    oracle's own decoder reads the stream back to the same pixels."""
+    from test_gpu_parity import compare_all
+    img = pkg.synth_image(w, h, 11 + w)
+    flags = pkg.FLAG_GABORISH
+    stages = ("xyb", "mask1x1", "homog", "acs", "raw_qf", "dc_quant", "nzeros", "coeffs", "codestream")
+    if proposal == 0:
+        stages = tuple(s for s in stages if s != "homog")      # (only the proposals compute the map on the device)
+    compare_all(pkg, oracle, encoder, img, distance, 7, proposal, flags, stages)
+    data, st = encoder.encode(img, distance, 7, proposal, flags | pkg.FLAG_QUALITY)
+    ora = oracle.encode(img, distance, 7, proposal, flags)
+    assert st.sse == [int(v) for v in ora.sse(img)]
+    plain, _ = encoder.encode(img, distance, 7, proposal, 0)
+    assert plain != data
+    dec = oracle.decode_pixels(data, w, h)
+    sse = ((dec.astype(np.int64) - img.astype(np.int64)) ** 2).reshape(-1, 3).sum(0)
+    assert [int(v) for v in sse] == st.sse

@@ -172,3 +172,27 @@ def test_xyb_matches_the_float64_definition(oracle, pkg):
     lms = np.cbrt(mix) - np.cbrt(bias)
     want = np.stack([(lms[..., 0] - lms[..., 1]) / 2, (lms[..., 0] + lms[..., 1]) / 2, lms[..., 2]])
     assert np.abs(xyb - want).max() < 1e-5
+
+
+def test_gaborish_round_trip_and_kernel(pkg, oracle):
+    """Row U3 (opt-in): the encoder's 5x5 kernel is the least-squares inverse of the decoder's default 3x3 Gaborish kernel
+    (tools/gen_gab_inverse.py): sharpening then blurring a smooth image returns it to within 1 %; the flag sets the loop
+    filter bit, the self-decoder applies the blur, and the decoded pixels equal the encoder-side reconstruction."""
+    import subprocess, sys, os, re
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "gen_gab_inverse.py")],
+                         capture_output=True, text=True, check=True).stdout
+    weights = [float(v) for v in re.findall(r"([-0-9.e+]+)f", out)]
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "jxo_xyb.cc")).read()
+    for wv in weights:
+        assert f"{np.float32(wv):.9e}f" in src
+    assert abs(weights[0] + 4 * (weights[1] + weights[2] + weights[3] + weights[5]) + 8 * weights[4] - 1.0) < 1e-6
+    img = pkg.synth_image(264, 200, 21)
+    a = oracle.encode(img, 1.0, 7, 0, 0)
+    b = oracle.encode(img, 1.0, 7, 0, 16)
+    assert b.error == "" and a.dump("codestream").tobytes() != b.dump("codestream").tobytes()
+    assert np.array_equal(a.dump("mask1x1"), b.dump("mask1x1"))            # the quant field stage uses the pre-sharpening planes
+    dec = oracle.decode_pixels(b.dump("codestream").tobytes(), 264, 200)
+    sse = ((dec.astype(np.int64) - img.astype(np.int64)) ** 2).reshape(-1, 3).sum(0)
+    assert [int(v) for v in sse] == [int(v) for v in b.sse(img)]
+    mse = float(sum(int(v) for v in sse)) / img.size
+    assert 10 * np.log10(255.0 ** 2 / mse) > 36.0

@@ -61,6 +61,7 @@ pub const JXLB200_FLAG_UNIFORM_QF: u32 = 2;
 pub const JXLB200_FLAG_QUALITY: u32 = 4;
 pub const JXLB200_FLAG_FORCED_ACS: u32 = 8;
 pub const JXLB200_FLAG_GABORISH: u32 = 16;
+pub const JXLB200_FLAG_CFL: u32 = 32;
 
 extern "C" {
     pub fn jxlb200_abi_version() -> c_int;

@@ -51,6 +51,8 @@ enum {
 #define JXLB200_FLAG_GABORISH 16u  /* Gaborish loop filter: signal the decoder's default 3x3 blur and sharpen the XYB planes with its
                                       5x5 least-squares inverse before the search (libjxl's default is on, with its own tuned
                                       kernel; off here unless asked for: SURVEY 8a row U3)                              */
+#define JXLB200_FLAG_CFL 32u       /* chroma from luma: fit ytox / ytob per 64x64 tile (ridge least squares on the weighted DCT8
+                                      coefficients; libjxl's own fit is not available offline) instead of the all-zero map  */
 
 /* Input image: 8-bit sRGB, interleaved RGB, row-major (what the harness hands to cjxl
  * as a PNG; image_reader.rs ColorType::Rgb8).  `stride` is bytes per row (>= 3*width). */

@@ -15,7 +15,7 @@ _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .encoder import (  # noqa: F401
     Encoder, EncodeError, Stats, PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY,
-    PROPOSAL_COMBINED, FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, FLAG_FORCED_ACS, FLAG_GABORISH, STAGES, frame_dims, library_path, load_library,
+    PROPOSAL_COMBINED, FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, FLAG_FORCED_ACS, FLAG_GABORISH, FLAG_CFL, STAGES, frame_dims, library_path, load_library,
 )
 from .synth import synth_image, synth_batch  # noqa: F401
 from .sharding import (  # noqa: F401

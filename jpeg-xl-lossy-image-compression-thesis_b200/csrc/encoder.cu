@@ -225,7 +225,7 @@ void Encoder::Destroy() {
   for (int k = 0; k < 4; ++k) { d_w8_[k].Release(); d_dq8_[k].Release(); }
   for (int k = 0; k < 6; ++k) { d_weights_c_[k].Release(); d_dequant_c_[k].Release(); }
   for (int k = 0; k < 11; ++k) { d_weights_j_[k].Release(); d_dequant_j_[k].Release(); d_inv_j_[k].Release(); }
-  d_xyb_gab_.Release();
+  d_xyb_gab_.Release(); d_cfl_.Release();
   d_acs_work_.Release(); d_acs_jobs_.Release(); d_coeff_lists_.Release(); d_recon_xyb_.Release();
   d_bias8_.Release(); d_lastlut8_.Release(); d_cvx_.Release(); d_cvy_.Release();
   for (int o = 0; o < 17; ++o) d_inv_order_[o].Release();
@@ -413,6 +413,12 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
   // `search` selects the general coefficient path (every strategy); the forced map takes it too
   const bool search = forced || (!(p.flags & JXLB200_FLAG_FIXED_DCT8) && p.effort >= 5);
   CUDA_OK(cudaMemsetAsync(d_cmap_.p, 0, (size_t)2 * fd.txs * fd.tys, stream_));
+  // chroma from luma (opt-in): per-tile factors fitted on the planes the search sees; the default map is all zero
+  const bool cfl = (p.flags & JXLB200_FLAG_CFL) != 0;
+  if (cfl) {
+    if (!d_cfl_.Reserve((size_t)fd.txs * fd.tys)) { *err = "device allocation failed"; return false; }
+    launch_cfl_fit(X, Y, B, fd, d_weights_[0].p, d_cmap_.p, d_cfl_.p, stream_);
+  }
   AcsTables tables;
   for (int k = 0; k < 17; ++k) {
     tables.w[k] = d_weights_[k].p; tables.dq[k] = d_dequant_[k].p; tables.wT[k] = d_weights_t_[k].p; tables.dqT[k] = d_dequant_t_[k].p;
@@ -431,11 +437,10 @@ bool Encoder::Run(const uint8_t* d_rgb, size_t stride, const EncodeParams& p, st
     ap.cost_delta = 10.833273317067883f * powf(ratio, 0.36702940662370243f);
     ap.distance = p.distance;
     ap.mul8x8 = 1.0f - 0.4f / (p.distance + 1.4f);
-    ap.cmap_x = 0.0f; ap.cmap_b = 1.0f;   // colour correlation map is the default (all tiles 0)
     ap.partitioning = p.proposal == JXLB200_PROPOSAL_PARTITIONING || p.proposal == JXLB200_PROPOSAL_COMBINED;
     ap.factored_entropy = p.proposal == JXLB200_PROPOSAL_FACTORED_ENTROPY || p.proposal == JXLB200_PROPOSAL_COMBINED;
     ap.speed_tier = 10 - (int)p.effort;
-    launch_acs(X, Y, B, d_mask1x1_.p, d_qf_.p, d_homog_.p, fd, ap, tables, d_acs_work_.p, d_acs_jobs_.p, d_acs_.p, d_acs_entropy_.p,
+    launch_acs(X, Y, B, d_mask1x1_.p, d_qf_.p, d_homog_.p, cfl ? d_cfl_.p : nullptr, fd, ap, tables, d_acs_work_.p, d_acs_jobs_.p, d_acs_.p, d_acs_entropy_.p,
                stream_);
   } else {
     CUDA_OK(cudaMemsetAsync(d_acs_.p, 0x80, nblk, stream_));

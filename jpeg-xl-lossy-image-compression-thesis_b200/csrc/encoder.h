@@ -67,6 +67,7 @@ class Encoder {
   cudaStream_t stream_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t ev_copy_ = nullptr;
+  DevBuf<float2> d_cfl_;              // JXLB200_FLAG_CFL: per-tile (x, b) factors the search reads
   DevBuf<float> d_xyb_gab_;           // JXLB200_FLAG_GABORISH: the sharpened planes every stage after the quant field reads
   const float* xyb_cur_ = nullptr;    // the planes the last encode's search saw (JXLB200_STAGE_XYB tap)
   bool fork_ = false;

@@ -28,7 +28,7 @@ void launch_dct8_quant_v4(const float* x, const float* y, const float* b, const 
                           cudaStream_t s);
 // K6 (k_acs.cu) / K7 general (k_coeff.cu)
 struct AcsParams {
-  float info_loss_multiplier, zeros_mul, cost_delta, distance, mul8x8, cmap_x, cmap_b;
+  float info_loss_multiplier, zeros_mul, cost_delta, distance, mul8x8;
   int factored_entropy, partitioning;   // H9 / H8 hooks of the thesis' proposals
   int speed_tier;                       // 10 - effort (libjxl SpeedTier: hare = 5 ... tortoise = 1)
 };
@@ -46,8 +46,11 @@ struct AcsTables {
 };
 size_t acs_work_floats(const FrameDim& fd);   // candidate-value tables of the search
 size_t acs_work_jobs(const FrameDim& fd);     // counters + lists of the non-aligned squares (uint32 words)
+// chroma from luma (opt-in JXLB200_FLAG_CFL): per-tile ytox / ytob from the planes the search sees; w8 = DCT8 quantisation weights
+void launch_cfl_fit(const float* x, const float* y, const float* b, const FrameDim& fd, const float* w8, int8_t* cmap, float2* factors,
+                    cudaStream_t s);
 void launch_acs(const float* x, const float* y, const float* b, const float* mask1x1, const float* qf, const float* homog,
-                const FrameDim& fd, const AcsParams& P, const AcsTables& T, float* work, uint32_t* jobs, uint8_t* acs, float* est,
+                const float2* cfl /* per-tile factors of launch_cfl_fit, or nullptr for the default map */, const FrameDim& fd, const AcsParams& P, const AcsTables& T, float* work, uint32_t* jobs, uint8_t* acs, float* est,
                 cudaStream_t s);
 // two auxiliary streams + the events that order them against the main stream (nullptr: everything on the main stream)
 struct StreamFork { cudaStream_t aux[2]; cudaEvent_t fork, join[2]; };

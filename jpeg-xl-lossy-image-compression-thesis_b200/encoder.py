@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 PROPOSAL_NONE, PROPOSAL_PARTITIONING, PROPOSAL_FACTORED_ENTROPY, PROPOSAL_COMBINED = 0, 1, 2, 3
-FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, FLAG_FORCED_ACS, FLAG_GABORISH = 1, 2, 4, 8, 16
+FLAG_FIXED_DCT8, FLAG_UNIFORM_QF, FLAG_QUALITY, FLAG_FORCED_ACS, FLAG_GABORISH, FLAG_CFL = 1, 2, 4, 8, 16, 32
 
 # stage id -> (name, numpy dtype)   (JXLB200_STAGE_* in include/jxlb200.h)
 STAGES = {

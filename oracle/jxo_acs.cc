@@ -59,6 +59,49 @@ float ButterflySum(const float* lanes, int n) {
   return p[0];
 }
 
+}  // namespace
+
+// Chroma from luma (row U3, opt-in: kFlagCfl) — per 64x64 tile the factors ytox / ytob (int8, units of 1/84) that the
+// search, the coefficient stage and the decoder apply as X -= (0 + ytox/84) Y, B -= (1 + ytob/84) Y.  libjxl fits them in
+// enc_chroma_from_luma.cc with a robust iteration whose constants are not available offline; any map is a legal encoder
+// choice.  This is the ridge least-squares fit on the quantiser-weighted DCT8 AC coefficients of the tile's blocks:
+//   a_k = w_c[k] Y_k,  r_k = w_c[k] (C_k - base_c Y_k),  factor_c = sum(a r) / (sum(a a) + 0.25 n),  n = 63 x blocks,
+// every block's partial sums sequential over k = 1..63 (fused multiply-adds), the tile's sums a butterfly over its
+// 64 block slots (absent blocks add 0) — the order the CUDA kernel (k_cfl_fit) reproduces bit for bit.
+void ChromaFromLumaFit(Frame* f) {
+  const FrameDim& fd = f->fd;
+  const EncTables& T = GetTables();
+  const float* w = T.weights[0].data();   // DCT8, [c * 64 + position]
+  for (int ty = 0; ty < fd.tys; ++ty) for (int tx = 0; tx < fd.txs; ++tx) {
+    float sxy[64], sxx[64], sby[64], sbb[64];
+    int blocks = 0;
+    for (int i = 0; i < 64; ++i) {
+      sxy[i] = sxx[i] = sby[i] = sbb[i] = 0.0f;
+      const int bx = tx * 8 + (i & 7), by = ty * 8 + (i >> 3);
+      if (bx >= fd.bxs || by >= fd.bys) continue;
+      ++blocks;
+      float cf[3][64];
+      for (int c = 0; c < 3; ++c) TransformFromPixels(DCT, &f->xyb[c][(size_t)by * 8 * fd.pitch + (size_t)bx * 8], fd.pitch, cf[c]);
+      float axy = 0.0f, axx = 0.0f, aby = 0.0f, abb = 0.0f;
+      for (int k = 1; k < 64; ++k) {
+        const float ax = w[k] * cf[1][k], rx = w[k] * cf[0][k];
+        axy = fmaf(ax, rx, axy); axx = fmaf(ax, ax, axx);
+        const float ab = w[128 + k] * cf[1][k], rb = w[128 + k] * (cf[2][k] - cf[1][k]);
+        aby = fmaf(ab, rb, aby); abb = fmaf(ab, ab, abb);
+      }
+      sxy[i] = axy; sxx[i] = axx; sby[i] = aby; sbb[i] = abb;
+    }
+    const float ridge = 0.25f * (float)(63 * blocks);
+    const float fx = ButterflySum(sxy, 64) / (ButterflySum(sxx, 64) + ridge);
+    const float fb = ButterflySum(sby, 64) / (ButterflySum(sbb, 64) + ridge);
+    auto to_i8 = [](float v) { const float r = rintf(v * 84.0f); return (int8_t)(r < -128.0f ? -128.0f : (r > 127.0f ? 127.0f : r)); };
+    f->cmap[(size_t)ty * fd.txs + tx] = to_i8(fx);
+    f->cmap[(size_t)fd.txs * fd.tys + (size_t)ty * fd.txs + tx] = to_i8(fb);
+  }
+}
+
+namespace {
+
 inline bool IsPlainDct(int s) {
   return s == DCT || s == DCT16X16 || s == DCT32X32 || (s >= DCT16X8 && s <= DCT16X32) || (s >= DCT64X64 && s <= DCT32X64);
 }

@@ -133,6 +133,7 @@ bool EncodeFrame(const uint8_t* rgb, int w, int h, size_t stride, const Params& 
   HomogeneityMap(f);
 
   f->cmap.assign((size_t)2 * fd.txs * fd.tys, 0);
+  if (p.flags & kFlagCfl) ChromaFromLumaFit(f);   // (opt-in; on the planes the search sees)
   f->acs.assign(nblk, 0x80 | DCT);
   f->acs_entropy.assign(nblk, 0.0f);
   if (p.flags & kFlagForcedAcs) {

@@ -12,7 +12,7 @@ struct Params {
   uint32_t proposal = 0;  // 0 none, 1 partitioning, 2 factored-entropy, 3 combined
   uint32_t flags = 0;     // bit0: fixed DCT8 strategy; bit1: uniform quant field
 };
-enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u, kFlagForcedAcs = 8u, kFlagGaborish = 16u };
+enum : uint32_t { kFlagFixedDct8 = 1u, kFlagUniformQf = 2u, kFlagForcedAcs = 8u, kFlagGaborish = 16u, kFlagCfl = 32u };
 
 // stage ids — identical to JXLB200_STAGE_* in include/jxlb200.h
 enum Stage : int {

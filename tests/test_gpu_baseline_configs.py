@@ -215,3 +215,23 @@ def test_gaborish_parity(pkg, oracle, encoder, w, h, distance, proposal):
     dec = oracle.decode_pixels(data, w, h)
     sse = ((dec.astype(np.int64) - img.astype(np.int64)) ** 2).reshape(-1, 3).sum(0)
     assert [int(v) for v in sse] == st.sse
+
+
+@pytest.mark.parametrize("w,h,distance,proposal,extra", [(520, 392, 1.0, 3, 0), (264, 200, 3.0, 0, 16), (100, 60, 0.5, 2, 0),
+                                                         (1000, 700, 2.0, 1, 16), (264, 136, 1.0, 0, 1)])
+def test_chroma_from_luma_parity(pkg, oracle, encoder, w, h, distance, proposal, extra):
+    """Row U3 (opt-in JXLB200_FLAG_CFL): the fitted colour-correlation map, the search that applies it per tile (the X channel's
+    chroma-from-luma path is live here), coefficients, the map's modular stream, the codestream and the quality statistics
+    equal the oracle's — alone, with Gaborish, and on the fixed-DCT8 path; the oracle's decoder reads the stream back."""
+    from test_gpu_parity import compare_all
+    img = pkg.synth_image(w, h, 31 + w)
+    flags = pkg.FLAG_CFL | extra
+    stages = ("cmap", "acs", "raw_qf", "dc_quant", "nzeros", "coeffs", "codestream")
+    compare_all(pkg, oracle, encoder, img, distance, 7, proposal, flags, stages)
+    assert np.any(encoder.dump("cmap") != 0)
+    data, st = encoder.encode(img, distance, 7, proposal, flags | pkg.FLAG_QUALITY)
+    ora = oracle.encode(img, distance, 7, proposal, flags)
+    assert st.sse == [int(v) for v in ora.sse(img)]
+    dec = oracle.decode_pixels(data, w, h)
+    sse = ((dec.astype(np.int64) - img.astype(np.int64)) ** 2).reshape(-1, 3).sum(0)
+    assert [int(v) for v in sse] == st.sse

@@ -189,7 +189,7 @@ def main():
     pins = []
     for (w, h, idx, d, effort, proposal, flags) in [(64, 64, 1, 1.0, 7, 0, 1), (264, 136, 2, 1.0, 7, 0, 1), (256, 256, 3, 2.0, 7, 0, 0),
                                                     (200, 120, 4, 1.0, 7, 1, 0), (200, 120, 4, 1.0, 7, 2, 0), (200, 120, 4, 1.0, 7, 3, 0),
-                                                    (96, 72, 5, 8.0, 5, 3, 0), (200, 120, 4, 1.0, 7, 3, 16)]:
+                                                    (96, 72, 5, 8.0, 5, 3, 0), (200, 120, 4, 1.0, 7, 3, 16), (200, 120, 4, 1.0, 7, 3, 32)]:
         fr = ora.encode(pkg.synth_image(w, h, idx), d, effort, proposal, flags)
         cs = fr.dump("codestream").tobytes()
         pins.append({"w": w, "h": h, "index": idx, "distance": d, "effort": effort, "proposal": proposal, "flags": flags,

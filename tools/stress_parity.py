@@ -35,7 +35,7 @@ with pkg.Encoder(0) as enc:
         distance = float(np.round(np.exp(rng.uniform(np.log(0.05), np.log(20.0))), 3))
         effort = int(rng.choice([3, 5, 7, 9]))
         proposal = int(rng.integers(0, 4))
-        flags = int(rng.choice([0, 0, 1, 2, 3])) | (pkg.FLAG_GABORISH if rng.random() < 0.25 else 0)
+        flags = int(rng.choice([0, 0, 1, 2, 3])) | (pkg.FLAG_GABORISH if rng.random() < 0.25 else 0) | (pkg.FLAG_CFL if rng.random() < 0.3 else 0)
         data, st = enc.encode(img, distance, effort, proposal, flags | pkg.FLAG_QUALITY)
         f = ora.encode(img, distance, effort, proposal, flags)
         want = f.dump("codestream").tobytes()

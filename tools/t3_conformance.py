@@ -26,7 +26,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = "jpeg-xl-lossy-image-compression-thesis_b200"
-CASES = [(512, 512, 1.0, 7, 0), (1920, 1080, 0.5, 7, 3), (1920, 1080, 3.0, 7, 3), (3840, 2160, 1.0, 7, 1), (200, 120, 8.0, 5, 2)]
+# (w, h, distance, effort, proposal, flags); flags 48 = JXLB200_FLAG_GABORISH | JXLB200_FLAG_CFL, the loop filter and the colour
+# correlation map that cjxl's defaults use (with this repo's own sharpening kernel and fit: the bpp / metric deltas of those
+# cases measure exactly that difference)
+CASES = [(512, 512, 1.0, 7, 0, 0), (1920, 1080, 0.5, 7, 3, 0), (1920, 1080, 3.0, 7, 3, 0), (3840, 2160, 1.0, 7, 1, 0),
+         (200, 120, 8.0, 5, 2, 0), (512, 512, 1.0, 7, 0, 16), (512, 512, 1.0, 7, 0, 32), (1920, 1080, 1.0, 7, 0, 48)]
+
+# What this harness is the first chance to check (none of it can be pinned offline; DESIGN.md sections 2 and 3):
+#  * every [UPSTREAM] table and constant of the U-rows: quant weights, coefficient orders, context tables, AQ constants,
+#    the entropy-cost multipliers of the search, the default Gaborish weights the decoder applies;
+#  * the numerics the diffs leave open: contraction of `acc += a * b` in the proposals' scalar loops (fused here),
+#    `sqrt` / `0.3 * sqrt` evaluated in double, the planes' pitch and padded height used as `src_stride` / `src_ysize`;
+#  * the defined-behaviour choices at row / column 0 of the modified Laplacian and in TryMergeAcs.
 
 
 def find_tool(name):
@@ -79,14 +90,14 @@ def main():
     pkg = importlib.import_module(PKG)
     results, ok = [], True
     with pkg.Encoder(0) as enc, tempfile.TemporaryDirectory() as tmp:
-        for i, (w, h, d, e, prop) in enumerate(CASES):
+        for i, (w, h, d, e, prop, fl) in enumerate(CASES):
             img = pkg.synth_image(w, h, 500 + i)
-            data, st = enc.encode(img, d, e, prop, pkg.FLAG_QUALITY)
+            data, st = enc.encode(img, d, e, prop, pkg.FLAG_QUALITY | fl)
             src, jxl, dec = (os.path.join(tmp, f"{i}.{x}") for x in ("ppm", "jxl", "dec.ppm"))
             write_ppm(src, img)
             open(jxl, "wb").write(data)
             r = subprocess.run([djxl, jxl, dec], capture_output=True, text=True)
-            rec = {"case": [w, h, d, e, prop], "bytes": len(data), "bpp": st.bpp, "djxl_rc": r.returncode}
+            rec = {"case": [w, h, d, e, prop, fl], "bytes": len(data), "bpp": st.bpp, "djxl_rc": r.returncode}
             if r.returncode != 0:
                 rec["djxl_stderr"] = r.stderr[-400:]
                 ok = False

@@ -15,8 +15,9 @@ enc.set_strategy_map(acs)
 P, B = 32, 128
 enc.set_pipelines(P)
 ptrs = [d.data_ptr()] * B
-MODES = os.environ.get("EXP_MODES", "full,forced_map,fixed_dct8,effort5,full_noproposal").split(",")
-for name, effort, prop, flags in (("full", 7, 3, 0), ("forced_map", 7, 3, pkg.FLAG_FORCED_ACS), ("fixed_dct8", 7, 3, pkg.FLAG_FIXED_DCT8), ("effort5", 5, 3, 0), ("full_noproposal", 7, 0, 0)):
+MODES = os.environ.get("EXP_MODES", "full,forced_map,fixed_dct8,effort5,full_noproposal,full_gab_cfl").split(",")
+for name, effort, prop, flags in (("full", 7, 3, 0), ("forced_map", 7, 3, pkg.FLAG_FORCED_ACS), ("fixed_dct8", 7, 3, pkg.FLAG_FIXED_DCT8), ("effort5", 5, 3, 0), ("full_noproposal", 7, 0, 0),
+                                   ("full_gab_cfl", 7, 3, pkg.FLAG_GABORISH | pkg.FLAG_CFL)):
     if name not in MODES:
         continue
     for _ in range(2):

@@ -235,3 +235,26 @@ def test_chroma_from_luma_parity(pkg, oracle, encoder, w, h, distance, proposal,
     dec = oracle.decode_pixels(data, w, h)
     sse = ((dec.astype(np.int64) - img.astype(np.int64)) ** 2).reshape(-1, 3).sum(0)
     assert [int(v) for v in sse] == st.sse
+
+
+def test_optional_filters_in_batch_mode_and_forced_map_at_low_effort(pkg, oracle, encoder):
+    """A batch with JXLB200_FLAG_GABORISH | JXLB200_FLAG_CFL on four pipelines gives the single encodes' bytes (per-pipeline
+    sharpened planes and factor tables); a forced strategy map below effort 5 (no quant adjustment in the coefficient
+    stage) equals the oracle."""
+    from test_oracle_entropy import every_strategy_map
+    flags = pkg.FLAG_GABORISH | pkg.FLAG_CFL
+    imgs = [pkg.synth_image(264 + 8 * i, 200, 60 + i) for i in range(6)]
+    with pkg.Encoder(0) as enc:
+        enc.set_pipelines(4)
+        datas, _ = enc.encode_batch(imgs, [0.5, 1.0, 2.0, 1.0, 3.0, 1.5], 7, 3, flags)
+    for img, data, d in zip(imgs, datas, [0.5, 1.0, 2.0, 1.0, 3.0, 1.5]):
+        assert np.array_equal(np.frombuffer(data, dtype=np.uint8), oracle.encode(img, d, 7, 3, flags).dump("codestream"))
+    w, h = 264, 200
+    dd = pkg.frame_dims(w, h)
+    acs = every_strategy_map(dd["bys"], dd["bxs"], seed=11)
+    img = pkg.synth_image(w, h, 5)
+    encoder.set_strategy_map(acs)
+    data, st = encoder.encode(img, 1.0, 3, 0, pkg.FLAG_FORCED_ACS | pkg.FLAG_QUALITY)
+    ora = oracle.encode_forced(img, acs, 1.0, 3, 0, 0)
+    assert np.array_equal(np.frombuffer(data, dtype=np.uint8), ora.dump("codestream"))
+    assert st.sse == [int(v) for v in ora.sse(img)]

@@ -550,18 +550,38 @@ __global__ void __launch_bounds__(kAnsWarps * 32) k_ans_groups(const uint32_t* _
   uint32_t* s_states = reinterpret_cast<uint32_t*>(s_ops + kAnsWarps * 64);                  // [warps][32]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(rmap_g);
-    uint4* dst = reinterpret_cast<uint4*>(s_rmap);
-    // (eight 16-byte loads in flight per thread: the copy is 192 KB from L2 and every chain of the CTA waits for it)
-    const int n16 = K * kAnsTabSize / 8;
-    for (int i0 = 0; i0 < n16; i0 += 8 * kAnsWarps * 32) {
-      uint4 tmp[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { const int i = i0 + k * kAnsWarps * 32 + t; if (i < n16) tmp[k] = __ldg(src + i); }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { const int i = i0 + k * kAnsWarps * 32 + t; if (i < n16) dst[i] = tmp[k]; }
+    // The CTA's tables — K reverse maps of 8 KB and the context map, up to 199 KB, contiguous in global memory — are
+    // brought in by the copy engine: one thread issues bulk asynchronous copies (cp.async.bulk, 32 KB each) that complete
+    // on an mbarrier, every thread waits on its phase.  (The per-thread LDG -> STS loop this replaces took 48 round
+    // trips to L2 per thread before any chain could start.)
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (t == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = t; i < kNumAcContexts; i += kAnsWarps * 32) s_cmap[i] = cmap_g[i];
+    __syncthreads();
+    if (t == 0) {
+      const uint32_t bytes_r = (uint32_t)K * kAnsTabSize * 2, bytes_c = 7440;   // (the context map buffer is padded past 7425)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes_r + bytes_c) : "memory");
+      const uint32_t dst_r = (uint32_t)__cvta_generic_to_shared(s_rmap);
+      for (uint32_t off = 0; off < bytes_r; off += 32768u) {
+        const uint32_t n = min(32768u, bytes_r - off);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst_r + off), "l"(reinterpret_cast<const uint8_t*>(rmap_g) + off), "r"(n), "r"(mbar) : "memory");
+      }
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(s_cmap)), "l"(cmap_g), "r"(bytes_c), "r"(mbar) : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "ANS_TABLES_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra ANS_TABLES_DONE;\n"
+        "bra ANS_TABLES_WAIT;\n"
+        "ANS_TABLES_DONE:\n"
+        "}\n" ::"r"(mbar) : "memory");
   }
   __syncthreads();
   const uint32_t rmap_saddr = (uint32_t)__cvta_generic_to_shared(s_rmap);

@@ -396,7 +396,7 @@ def main():
                 "ms": acs_ms, "warp_instructions": inst, "achieved_Ginst_per_s": inst / (acs_ms / 1e3) / 1e9 if acs_ms > 0 else 0.0,
                 "peak_Ginst_per_s": PEAK_WARP_INST_PER_S / 1e9,
                 "frac": inst / (acs_ms / 1e3) / PEAK_WARP_INST_PER_S if acs_ms > 0 else 0.0,
-                "source": "warp instructions per pixel from ncu smsp__inst_executed.sum (profiles/r02c_inst_1080p.csv)"}
+                "source": "warp instructions per pixel from ncu smsp__inst_executed.sum (profiles/r02m_launches_1080p.csv)"}
         if k7 is not None:
             roof["k7_dct8"] = k7
         line = {

@@ -1,4 +1,4 @@
-"""Randomised parity sweep: random sizes (1..400), seeds, distances (0.05..20), efforts, proposals and flags; the CUDA
+"""Randomised parity sweep: random sizes (1..400 x 1..300 unless $STRESS_MAXW / $STRESS_MAXH say otherwise), seeds, distances (0.05..20), efforts, proposals and flags; the CUDA
 path's codestream and quality statistics must equal the oracle's for every case.  Images mix the synthetic generator with
 random rectangles, pure noise, black and saturated areas.  Usage: python tools/stress_parity.py [cases] [seed]"""
 import importlib
@@ -14,13 +14,14 @@ pkg = importlib.import_module("jpeg-xl-lossy-image-compression-thesis_b200")
 import oracle_lib
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+MAXW, MAXH = int(os.environ.get("STRESS_MAXW", 400)), int(os.environ.get("STRESS_MAXH", 300))   # e.g. 2300 x 2200: frames that cross a DC group
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 ora = oracle_lib.load(rebuild=False)
 t0 = time.perf_counter()
 bad = 0
 with pkg.Encoder(0) as enc:
     for i in range(N):
-        w, h = int(rng.integers(1, 400)), int(rng.integers(1, 300))
+        w, h = int(rng.integers(1, MAXW)), int(rng.integers(1, MAXH))
         img = pkg.synth_image(w, h, int(rng.integers(0, 1 << 30))).copy()
         kind = int(rng.integers(0, 5))
         if kind == 1:

@@ -28,9 +28,10 @@ constexpr int kHPitch = 264 + 8;                                     // 258 colu
 __device__ __forceinline__ int hidx(int c) { return c + (c >> 5); }  // padded column index
 
 // one sub-rectangle (XS x YS at (OX, OY) inside the block) of block `cb / 8`: CalculateHomogeneity (diff :153-181)
-template <int XS, int YS, int OX, int OY>
-__device__ __forceinline__ float homogeneity_rect(const float (*ssml)[kHPitch], const float (*sx)[kHPitch], const float (*sb)[kHPitch],
-                                                  const uint8_t* rowmask, const uint8_t* colmask, int cb) {
+// (the offsets are run-time values: three copies of the code — 8x4, 4x8, 4x4 — instead of eight, for the instruction cache)
+template <int XS, int YS>
+__device__ __noinline__ float homogeneity_rect(const float (*ssml)[kHPitch], const float (*sx)[kHPitch], const float (*sb)[kHPitch],
+                                                  const uint8_t* rowmask, const uint8_t* colmask, int cb, int OX, int OY) {
   // zero crossings (diff :17-55): rising edges of `laplacian > threshold` along the rows, then along the columns
   unsigned nh = 0, nv = 0;
 #pragma unroll
@@ -162,16 +163,11 @@ __global__ void __launch_bounds__(256) k_homogeneity(const float* __restrict__ X
     const int cb = lane * 8;
     const uint8_t* rmk = srow[lane]; const uint8_t* cmk = scol[lane];
     float h;
-    switch (warp) {   // (xsize, ysize, bx, by) of the eight calls
-      case 0: h = homogeneity_rect<8, 4, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 1: h = homogeneity_rect<8, 4, 0, 4>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 2: h = homogeneity_rect<4, 8, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 3: h = homogeneity_rect<4, 8, 4, 0>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 4: h = homogeneity_rect<4, 4, 0, 0>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 5: h = homogeneity_rect<4, 4, 4, 4>(ssml, sx, sb, rmk, cmk, cb); break;
-      case 6: h = homogeneity_rect<4, 4, 0, 4>(ssml, sx, sb, rmk, cmk, cb); break;
-      default: h = homogeneity_rect<4, 4, 4, 0>(ssml, sx, sb, rmk, cmk, cb); break;
-    }
+    // (xsize, ysize, bx, by) of the eight calls: warps 0-1 8x4 at y = 0 / 4, warps 2-3 4x8 at x = 0 / 4, warps 4-7 4x4 at
+    // (0,0), (4,4), (0,4), (4,0)
+    if (warp < 2) h = homogeneity_rect<8, 4>(ssml, sx, sb, rmk, cmk, cb, 0, warp * 4);
+    else if (warp < 4) h = homogeneity_rect<4, 8>(ssml, sx, sb, rmk, cmk, cb, (warp - 2) * 4, 0);
+    else h = homogeneity_rect<4, 4>(ssml, sx, sb, rmk, cmk, cb, (warp == 5 || warp == 7) ? 4 : 0, (warp == 5 || warp == 6) ? 4 : 0);
     sh[lane][warp] = h;
   }
   __syncthreads();

@@ -59,6 +59,14 @@ impl B200Encoder {
         self
     }
 
+    /// `cjxl`'s defaults have the Gaborish loop filter and chroma-from-luma fitting on; here they are opt-in
+    /// (`JXLB200_FLAG_GABORISH`, `JXLB200_FLAG_CFL`: this library's own sharpening kernel and fit).
+    pub fn with_loop_filter_and_cfl(mut self, gaborish: bool, cfl: bool) -> Self {
+        if gaborish { self.flags |= sys::JXLB200_FLAG_GABORISH; }
+        if cfl { self.flags |= sys::JXLB200_FLAG_CFL; }
+        self
+    }
+
     fn last_error(&self) -> String {
         unsafe { CStr::from_ptr(sys::jxlb200_last_error(self.ctx)) }.to_string_lossy().into_owned()
     }
